@@ -1,0 +1,23 @@
+# Builds libcoverage_cuda.so (sm_100a) and the CPU oracle (test infrastructure).
+NVCC      ?= /usr/local/cuda/bin/nvcc
+GCC       ?= /usr/bin/gcc
+PKG       := maximumareacoverageoptimization.jl_b200
+CSRC      := $(PKG)/csrc
+LIB       := $(PKG)/libcoverage_cuda.so
+ORACLE    := oracle/libcoverage_oracle.so
+NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --fmad=false \
+             -Xcompiler -fPIC,-O2,-fno-fast-math,-ffp-contract=off,-fvisibility=hidden,-pthread -Xptxas -v
+SRCS      := $(CSRC)/cov_api.cu $(CSRC)/cov_kernels.cu $(CSRC)/cov_grid_kernels.cu
+HDRS      := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh) include/coverage_cuda.h
+
+all: $(LIB) $(ORACLE)
+
+$(LIB): $(SRCS) $(HDRS)
+	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(SRCS) -cudart static
+
+$(ORACLE): oracle/coverage_oracle.c
+	$(GCC) -O2 -fPIC -shared -pthread -ffp-contract=off -fno-fast-math -fvisibility=hidden -o $@ $< -lm
+
+clean:
+	rm -f $(LIB) $(ORACLE)
+.PHONY: all clean

@@ -1,0 +1,102 @@
+"""Host-side mirror of the reference module `TDM_STATIC_opt`
+(/root/reference/src/TDM_STATIC_opt.jl): `createObjective(cells, N, r_max)` returns the closure
+`AreaMaxObjective(x)` with the reference's value semantics; the closure additionally exposes
+`.batch(X)` (a whole MADS poll set in one cov_eval_batch call) and `.fuse(constraints)`.
+`optimize(...)` is in mads.py (the batched poll driver) and re-exported here.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .CellFunctions import Cells
+from .AreaCoverageCalculation import PointList, ResidentList
+
+
+class AreaMaxObjective:
+    """src/TDM_STATIC_opt.jl:83-98:  -calculateArea(x, cells.points_of_interest)
+    + 1e5 * sum_i abs(x[i+2N] - r_max[i])."""
+
+    def __init__(self, cells, N: int, r_max):
+        self.cells = cells
+        self.N = int(N)
+        self.r_max = r_max  # captured by reference, like the Julia closure
+        self._fused = {}
+        self._param_key = None
+
+    def _resident(self) -> ResidentList:
+        c = self.cells
+        if isinstance(c, Cells):
+            return c.resident()
+        if isinstance(c, ResidentList):
+            return c
+        if not hasattr(self, "_own"):
+            self._own = ResidentList(PointList.infer(c))
+        return self._own
+
+    def fuse(self, constraints):
+        """Fold extreme constraints that carry a `.fuse` description (create_cons3/7/8, cons1) into
+        this objective's kernel launch; returns the ones that stay host callables."""
+        rest = []
+        fused = {}
+        for c in constraints:
+            f = getattr(c, "fuse", None)
+            if f is None:
+                rest.append(c)
+            else:
+                fused.update(f)
+        self._fused = fused
+        self._param_key = None
+        return rest
+
+    def _engine(self):
+        res = self._resident()
+        eng = res.sync()
+        r = np.ascontiguousarray(self.r_max, dtype=np.float64).ravel()
+        key = (r.tobytes(), id(self._fused))
+        if self._param_key != key or eng.N != self.N:
+            eng.set_params(self.N, r, 1e5, **self._fused)
+            self._param_key = key
+        return res, eng
+
+    def batch(self, X, want_feasible=False):
+        """Objective of every row of X (B x 3N).  With want_feasible also the fused extreme
+        constraints' verdicts."""
+        res, eng = self._engine()
+        X = np.ascontiguousarray(X, dtype=np.float64).reshape(-1, 3 * self.N)
+        info = eng.grid_info()
+        if not info["area_exact"]:
+            # order-dependent Float64 sum (non-dyadic weights): per-candidate replay
+            obj = np.array([self._replay(res, x) for x in X])
+            if want_feasible:
+                return obj, eng.eval_batch(X, want_count=False)["feasible"].astype(bool)
+            return obj
+        out = eng.eval_batch(X, want_count=False, want_feasible=want_feasible)
+        if want_feasible:
+            return out["obj"], out["feasible"].astype(bool)
+        return out["obj"]
+
+    def _replay(self, res, x):
+        area, _ = res.area_and_count(x)
+        self._param_key = None  # area_and_count may have changed the engine's parameters
+        violation = 0.0
+        for i in range(self.N):
+            violation += abs(float(x[i + 2 * self.N]) - float(self.r_max[i]))
+        return -area + violation * 1e5
+
+    def __call__(self, x) -> float:
+        res, eng = self._engine()
+        x = np.ascontiguousarray(x, dtype=np.float64).ravel()
+        if not eng.grid_info()["area_exact"]:
+            return self._replay(res, x)
+        return eng.eval_one(x)
+
+
+def createObjective(cells, N, r_max) -> AreaMaxObjective:
+    """src/TDM_STATIC_opt.jl:82-100."""
+    return AreaMaxObjective(cells, N, r_max)
+
+
+def optimize(input, obj, cons_ext, cons_prog, N_iter, **kw):
+    """src/TDM_STATIC_opt.jl:118-222 -- see mads.optimize."""
+    from .mads import optimize as _opt
+    return _opt(input, obj, cons_ext, cons_prog, N_iter, **kw)

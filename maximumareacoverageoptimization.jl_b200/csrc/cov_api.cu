@@ -1,0 +1,1291 @@
+// cov_api.cu -- the C ABI of libcoverage_cuda (include/coverage_cuda.h): handle lifecycle, the
+// device-resident cell store, parameter upload, and the batched evaluation pipelines.
+//
+// The reference (/root/reference, pure Julia) has no FFI; each entry point replaces the Julia
+// lines cited beside its declaration in include/coverage_cuda.h. Nothing here computes coverage
+// on the CPU: without a CUDA device every entry point that needs one fails with COV_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+#include "cov_device.cuh"
+#include "cov_kernels.cuh"
+#include "../../include/coverage_cuda.h"
+
+using namespace cov;
+
+// ------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct cov_handle {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr; // stream = own_stream or an adopted one
+    cudaStream_t s_in = nullptr, s_out = nullptr;        // copy engines of the host pipeline
+    std::string err;
+
+    // cell store
+    bool have_grid = false;
+    DevBuf mult, cls, planes;
+    GridDesc g{};
+    int64_t n_entries = 0, n_cells = 0;
+    int area_exact = 0;
+
+    // closure parameters
+    bool have_params = false;
+    ObjParams o{};
+    DevBuf params; // 5N doubles: r_max, prev_x, prev_y, prev_z, cons3_G
+
+    LaunchCfg cfg{};
+    int64_t chunk = 0;
+
+    // scratch
+    DevBuf counter, stats, xyT, small_in, argmin_obj, argmin_idx, removed, overflow;
+    // evaluation window (device) and staging (pinned host)
+    DevBuf dX, d_obj, d_count, d_feas, d_clscnt, d_prog;
+    void *h_in[2] = {nullptr, nullptr};
+    size_t h_in_cap = 0;
+    void *h_out = nullptr;
+    size_t h_out_cap = 0;
+    void *h_small = nullptr; // pinned scratch: 4 KiB of scalars, then one candidate
+
+    std::vector<cudaEvent_t> ev_pool; // recycled
+    // (start, stop) events around every coverage-kernel launch since the last drain
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kernel_spans;
+    size_t last_call_begin = 0;   // first span of the last eval call
+    double drained_ms = 0;        // spans already folded into the running total
+    int64_t drained_launches = 0;
+    double last_call_ms_cache = -1;
+    int64_t launches = 0;
+    LaunchInfo last_info{};
+};
+
+static thread_local std::string g_err_nohandle;
+
+static int fail(cov_handle *h, int code, const std::string &msg)
+{
+    if (h) h->err = msg;
+    else g_err_nohandle = msg;
+    return code;
+}
+static int fail_cuda(cov_handle *h, cudaError_t e, const char *what)
+{
+    (void)cudaGetLastError(); // clear the sticky-free error state
+    return fail(h, COV_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CK(call)                                                 \
+    do {                                                         \
+        cudaError_t e_ = (call);                                 \
+        if (e_ != cudaSuccess) return fail_cuda(h, e_, #call);   \
+    } while (0)
+
+static int ensure(cov_handle *h, DevBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap && b.p) return COV_OK;
+    if (b.p) {
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    bytes = std::max<size_t>(bytes, 256);
+    cudaError_t e = cudaMalloc(&b.p, bytes);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        b.p = nullptr;
+        return fail(h, e == cudaErrorMemoryAllocation ? COV_ERR_NOMEM : COV_ERR_CUDA,
+                    std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+    }
+    b.cap = bytes;
+    return COV_OK;
+}
+#define OK(call)                   \
+    do {                           \
+        int rc_ = (call);          \
+        if (rc_ != COV_OK) return rc_; \
+    } while (0)
+
+static int ensure_pinned(cov_handle *h, void **p, size_t *cap, size_t bytes)
+{
+    if (*p && bytes <= *cap) return COV_OK;
+    if (*p) {
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaFreeHost(*p));
+        *p = nullptr;
+        *cap = 0;
+    }
+    cudaError_t e = cudaMallocHost(p, std::max<size_t>(bytes, 4096));
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        *p = nullptr;
+        return fail(h, COV_ERR_NOMEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+    }
+    *cap = std::max<size_t>(bytes, 4096);
+    return COV_OK;
+}
+
+static cudaEvent_t get_event(cov_handle *h)
+{
+    if (!h->ev_pool.empty()) {
+        cudaEvent_t e = h->ev_pool.back();
+        h->ev_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+// Fold every recorded span into the running totals (synchronises the main stream).
+static cudaError_t drain_spans(cov_handle *h)
+{
+    if (h->kernel_spans.empty()) return cudaSuccess;
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) return e;
+    double last = 0;
+    for (size_t k = 0; k < h->kernel_spans.size(); ++k) {
+        float t = 0;
+        e = cudaEventElapsedTime(&t, h->kernel_spans[k].first, h->kernel_spans[k].second);
+        if (e != cudaSuccess) return e;
+        h->drained_ms += t;
+        h->drained_launches += 1;
+        if (k >= h->last_call_begin) last += t;
+        h->ev_pool.push_back(h->kernel_spans[k].first);
+        h->ev_pool.push_back(h->kernel_spans[k].second);
+    }
+    h->last_call_ms_cache = last;
+    h->kernel_spans.clear();
+    h->last_call_begin = 0;
+    return cudaSuccess;
+}
+// A new eval call starts: remember where its spans begin; keep the event pool bounded.
+static void recycle_spans(cov_handle *h)
+{
+    if (h->kernel_spans.size() > 2048) (void)drain_spans(h);
+    h->last_call_begin = h->kernel_spans.size();
+    h->last_call_ms_cache = -1;
+}
+
+static bool is_pinned_host(const void *p)
+{
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// lifecycle
+// ------------------------------------------------------------------------------------------
+extern "C" int cov_abi_version(void) { return COV_ABI_VERSION; }
+
+extern "C" int cov_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int cov_create(int device, cov_handle **out)
+{
+    cov_handle *h = nullptr; // for the macros
+    if (!out) return fail(nullptr, COV_ERR_INVALID, "cov_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        (void)cudaGetLastError();
+        return fail(nullptr, COV_ERR_CUDA,
+                    std::string("cov_create: no usable CUDA device (") +
+                        (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                        "); libcoverage_cuda has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return fail(nullptr, COV_ERR_INVALID, "cov_create: device index out of range");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop{};
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(nullptr, COV_ERR_CUDA,
+                    std::string("cov_create: device ") + prop.name + " is sm_" + std::to_string(prop.major) +
+                        std::to_string(prop.minor) + "; this library is built for sm_100a only");
+    cov_handle *nh = new cov_handle();
+    nh->device = device;
+    h = nh;
+    auto bail = [&](cudaError_t ce, const char *what) {
+        int rc = fail_cuda(nullptr, ce, what);
+        delete nh;
+        return rc;
+    };
+    if ((e = cudaStreamCreateWithFlags(&nh->own_stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return bail(e, "cudaStreamCreate");
+    if ((e = cudaStreamCreateWithFlags(&nh->s_in, cudaStreamNonBlocking)) != cudaSuccess)
+        return bail(e, "cudaStreamCreate");
+    if ((e = cudaStreamCreateWithFlags(&nh->s_out, cudaStreamNonBlocking)) != cudaSuccess)
+        return bail(e, "cudaStreamCreate");
+    nh->stream = nh->own_stream;
+    nh->cfg.kernel = COV_KERNEL_AUTO;
+    nh->cfg.num_sms = prop.multiProcessorCount;
+    nh->cfg.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if ((e = cudaMallocHost(&nh->h_small, 4096 + 3 * kMaxUavs * 8)) != cudaSuccess) return bail(e, "cudaMallocHost");
+    int rc = ensure(nh, nh->counter, 256);
+    if (rc == COV_OK) rc = ensure(nh, nh->stats, 256);
+    if (rc == COV_OK) rc = ensure(nh, nh->removed, 256);
+    if (rc == COV_OK) rc = ensure(nh, nh->overflow, 256);
+    if (rc == COV_OK) rc = ensure(nh, nh->argmin_obj, 1024 * sizeof(double));
+    if (rc == COV_OK) rc = ensure(nh, nh->argmin_idx, 1024 * sizeof(long long));
+    if (rc != COV_OK) {
+        g_err_nohandle = nh->err;
+        delete nh;
+        return rc;
+    }
+    *out = nh;
+    return COV_OK;
+}
+
+extern "C" void cov_destroy(cov_handle *h)
+{
+    if (!h) return;
+    DeviceGuard dg(h->device);
+    cudaStreamSynchronize(h->stream);
+    cudaStreamSynchronize(h->s_in);
+    cudaStreamSynchronize(h->s_out);
+    DevBuf *bufs[] = {&h->mult, &h->cls, &h->planes, &h->params, &h->counter, &h->stats, &h->xyT,
+                      &h->small_in, &h->argmin_obj, &h->argmin_idx, &h->removed, &h->overflow, &h->dX,
+                      &h->d_obj, &h->d_count, &h->d_feas, &h->d_clscnt, &h->d_prog};
+    for (DevBuf *b : bufs)
+        if (b->p) cudaFree(b->p);
+    for (int k = 0; k < 2; ++k)
+        if (h->h_in[k]) cudaFreeHost(h->h_in[k]);
+    if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->h_small) cudaFreeHost(h->h_small);
+    (void)drain_spans(h);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    cudaStreamDestroy(h->s_in);
+    cudaStreamDestroy(h->s_out);
+    cudaStreamDestroy(h->own_stream);
+    (void)cudaGetLastError();
+    delete h;
+}
+
+extern "C" const char *cov_last_error(const cov_handle *h) { return h ? h->err.c_str() : g_err_nohandle.c_str(); }
+
+extern "C" int cov_set_option(cov_handle *h, int option, int64_t value)
+{
+    if (!h) return fail(nullptr, COV_ERR_INVALID, "cov_set_option: NULL handle");
+    switch (option) {
+    case COV_OPT_KERNEL:
+        if (value < COV_KERNEL_AUTO || value > COV_KERNEL_EXACT) return fail(h, COV_ERR_INVALID, "unknown kernel id");
+        h->cfg.kernel = (int)value;
+        return COV_OK;
+    case COV_OPT_WARPS_PER_CTA:
+        if (value < 0 || value > 32) return fail(h, COV_ERR_INVALID, "warps per CTA must be 0..32");
+        h->cfg.warps_per_cta = (int)value;
+        return COV_OK;
+    case COV_OPT_CTAS_PER_SM:
+        if (value < 0 || value > 32) return fail(h, COV_ERR_INVALID, "CTAs per SM must be 0..32");
+        h->cfg.ctas_per_sm = (int)value;
+        return COV_OK;
+    case COV_OPT_BAND_ROWS:
+        if (value < 0 || value > kMaxDim) return fail(h, COV_ERR_INVALID, "band rows out of range");
+        h->cfg.band_rows = (int)value;
+        return COV_OK;
+    case COV_OPT_FORCE_EXACT:
+        h->cfg.force_exact = value != 0;
+        return COV_OK;
+    case COV_OPT_CHUNK:
+        if (value < 0) return fail(h, COV_ERR_INVALID, "chunk must be >= 0");
+        h->chunk = value;
+        return COV_OK;
+    }
+    return fail(h, COV_ERR_INVALID, "unknown option");
+}
+
+extern "C" int cov_get_option(const cov_handle *h, int option, int64_t *value)
+{
+    if (!h || !value) return COV_ERR_INVALID;
+    switch (option) {
+    case COV_OPT_KERNEL: *value = h->cfg.kernel; return COV_OK;
+    case COV_OPT_WARPS_PER_CTA: *value = h->cfg.warps_per_cta; return COV_OK;
+    case COV_OPT_CTAS_PER_SM: *value = h->cfg.ctas_per_sm; return COV_OK;
+    case COV_OPT_BAND_ROWS: *value = h->cfg.band_rows; return COV_OK;
+    case COV_OPT_FORCE_EXACT: *value = h->cfg.force_exact; return COV_OK;
+    case COV_OPT_CHUNK: *value = h->chunk; return COV_OK;
+    }
+    return COV_ERR_INVALID;
+}
+
+extern "C" void cov_get_limits(cov_limits *out)
+{
+    if (!out) return;
+    out->max_uavs = kMaxUavs;
+    out->max_nx = kMaxDim;
+    out->max_ny = kMaxDim;
+    out->max_planes = kMaxPlanes;
+    out->max_classes = kMaxClasses;
+}
+
+extern "C" double cov_threshold(double R) { return threshold(R); }
+
+// ------------------------------------------------------------------------------------------
+// cell store
+// ------------------------------------------------------------------------------------------
+static bool f32_exact(double v) { return (double)(float)v == v; }
+
+static int check_lattice(cov_handle *h, int64_t nx, int64_t ny, double dx, double dy)
+{
+    if (nx < 1 || ny < 1) return fail(h, COV_ERR_INVALID, "grid: nx, ny must be >= 1");
+    if (nx > kMaxDim || ny > kMaxDim) return fail(h, COV_ERR_LIMIT, "grid: nx, ny must be <= 32768");
+    if (!(dx > 0) || !(dy > 0) || std::isinf(dx) || std::isinf(dy))
+        return fail(h, COV_ERR_INVALID, "grid: dx, dy must be finite and > 0");
+    return COV_OK;
+}
+
+static void describe_lattice(cov_handle *h, int64_t nx, int64_t ny, double dx, double dy)
+{
+    GridDesc &g = h->g;
+    g.nx = (int)nx;
+    g.ny = (int)ny;
+    g.wpr = (int)((nx + 31) / 32);
+    g.stride = g.wpr | 1; // odd: 32 lanes on 32 consecutive rows hit 32 different banks
+    g.plane_words = (int)(((int64_t)g.ny * g.stride + 3) / 4 * 4);
+    g.dx = dx;
+    g.dy = dy;
+    g.hdx = dx / 2;
+    g.hdy = dy / 2;
+    g.inv_dx = 1.0 / dx;
+    g.inv_dy = 1.0 / dy;
+    g.dxf = (float)dx;
+    g.dyf = (float)dy;
+    g.hdxf = (float)g.hdx;
+    g.hdyf = (float)g.hdy;
+    g.inv_dxf = (float)g.inv_dx;
+    g.inv_dyf = (float)g.inv_dy;
+    g.extent = (float)std::max((double)nx * dx, (double)ny * dy);
+    g.extent = std::nextafter(g.extent, INFINITY);
+    g.lattice_f32_exact = f32_exact(dx) && f32_exact(dy) && f32_exact(g.hdx) && f32_exact(g.hdy) &&
+                          f32_exact((double)nx * dx) && f32_exact((double)ny * dy);
+}
+
+// v = m * 2^e with m odd (v finite, > 0)
+static void odd_decompose(double v, uint64_t &m, int &e)
+{
+    int ex;
+    double fr = std::frexp(v, &ex); // v = fr * 2^ex, fr in [0.5, 1)
+    m = (uint64_t)std::ldexp(fr, 53);
+    e = ex - 53;
+    while (m && !(m & 1)) {
+        m >>= 1;
+        ++e;
+    }
+}
+
+// Derive the bit planes from the device-resident mult/cls bytes and refresh the statistics.
+static int rebuild_planes(cov_handle *h, int n_classes, const double *class_weight)
+{
+    GridDesc &g = h->g;
+    const long long ncell = (long long)g.nx * g.ny;
+    unsigned long long *d_stats = (unsigned long long *)h->stats.p;
+    CK(launch_grid_stats((const unsigned char *)h->mult.p, (const unsigned char *)h->cls.p, ncell, d_stats,
+                         h->stream));
+    h->launches += 1;
+    unsigned long long *hs = (unsigned long long *)h->h_small;
+    CK(cudaMemcpyAsync(hs, d_stats, (2 + kMaxClasses) * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                       h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->n_entries = (int64_t)hs[0];
+    h->n_cells = (int64_t)hs[1];
+    g.n_classes = std::max(1, n_classes);
+    for (int k = 0; k < kMaxClasses; ++k) g.class_weight[k] = (k < n_classes) ? class_weight[k] : 0.0;
+    int np = 0;
+    for (int k = 0; k < g.n_classes; ++k) {
+        const unsigned orm = (unsigned)hs[2 + k];
+        for (int b = 0; b < 8; ++b)
+            if (orm & (1u << b)) {
+                if (np >= kMaxPlanes)
+                    return fail(h, COV_ERR_LIMIT,
+                                "cell store needs more than 8 bit planes (weight classes x multiplicity bits)");
+                g.plane_class[np] = k;
+                g.plane_mult[np] = 1 << b;
+                ++np;
+            }
+    }
+    if (np == 0) { // empty store: one all-zero plane keeps the kernels uniform
+        g.plane_class[0] = 0;
+        g.plane_mult[0] = 1;
+        np = 1;
+    }
+    for (int l = np; l < kMaxPlanes; ++l) {
+        g.plane_class[l] = 0;
+        g.plane_mult[l] = 0;
+    }
+    g.n_planes = np;
+    OK(ensure(h, h->planes, (size_t)np * g.plane_words * 4));
+    g.planes = (const uint32_t *)h->planes.p;
+    CK(launch_pack_planes((const unsigned char *)h->mult.p, (const unsigned char *)h->cls.p, g,
+                          (uint32_t *)h->planes.p, h->stream));
+    h->launches += 1;
+    // area_exact: every partial sum of the reference's list-order Float64 accumulation is an
+    // integer multiple of a common power of two and stays below 2^53 of them, hence exact in any
+    // order, and so is sum_k fl(w_k * count_k).
+    h->area_exact = 1;
+    {
+        int qmin = 0;
+        bool first = true, ok = true;
+        uint64_t ms[kMaxClasses];
+        int es[kMaxClasses];
+        for (int k = 0; k < g.n_classes; ++k) {
+            const double w = g.class_weight[k];
+            if (w == 0.0) {
+                ms[k] = 0;
+                es[k] = 0;
+                continue;
+            }
+            if (!(w > 0) || std::isinf(w)) {
+                ok = false;
+                break;
+            }
+            odd_decompose(w, ms[k], es[k]);
+            if (first || es[k] < qmin) qmin = es[k];
+            first = false;
+        }
+        if (ok) {
+            long double total = 0;
+            for (int k = 0; k < g.n_classes; ++k)
+                if (ms[k]) total += std::ldexp((long double)ms[k], es[k] - qmin) * (long double)h->n_entries;
+            ok = total < 9007199254740992.0L;
+        }
+        h->area_exact = ok ? 1 : 0;
+    }
+    h->have_grid = true;
+    return COV_OK;
+}
+
+static int alloc_cells(cov_handle *h)
+{
+    const size_t ncell = (size_t)h->g.nx * h->g.ny;
+    OK(ensure(h, h->mult, ncell + 4)); // add_points works on aligned 4-byte words
+    OK(ensure(h, h->cls, ncell + 4));
+    return COV_OK;
+}
+
+extern "C" int cov_set_grid_bits(cov_handle *h, int64_t nx, int64_t ny, double dx, double dy,
+                                 const uint32_t *bits, double weight)
+{
+    if (!h) return fail(nullptr, COV_ERR_INVALID, "NULL handle");
+    DeviceGuard dg(h->device);
+    if (!bits) return fail(h, COV_ERR_INVALID, "cov_set_grid_bits: bits is NULL");
+    OK(check_lattice(h, nx, ny, dx, dy));
+    h->have_grid = false;
+    describe_lattice(h, nx, ny, dx, dy);
+    OK(alloc_cells(h));
+    const size_t words = (size_t)ny * ((nx + 31) / 32);
+    DevBuf tmp;
+    OK(ensure(h, tmp, words * 4));
+    cudaError_t e = cudaMemcpyAsync(tmp.p, bits, words * 4, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess)
+        e = launch_bits_to_cells((const uint32_t *)tmp.p, (int)nx, (int)ny, (unsigned char *)h->mult.p,
+                                 (unsigned char *)h->cls.p, h->stream);
+    h->launches += 1;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(tmp.p);
+    if (e != cudaSuccess) return fail_cuda(h, e, "cov_set_grid_bits");
+    return rebuild_planes(h, 1, &weight);
+}
+
+extern "C" int cov_set_grid_cells(cov_handle *h, int64_t nx, int64_t ny, double dx, double dy,
+                                  const uint8_t *mult, const uint8_t *cls, int64_t n_classes,
+                                  const double *class_weight)
+{
+    if (!h) return fail(nullptr, COV_ERR_INVALID, "NULL handle");
+    DeviceGuard dg(h->device);
+    if (!mult || !class_weight) return fail(h, COV_ERR_INVALID, "cov_set_grid_cells: NULL argument");
+    if (n_classes < 1 || n_classes > kMaxClasses)
+        return fail(h, COV_ERR_LIMIT, "cov_set_grid_cells: n_classes must be 1..4");
+    OK(check_lattice(h, nx, ny, dx, dy));
+    const size_t ncell = (size_t)nx * ny;
+    if (cls)
+        for (size_t t = 0; t < ncell; ++t)
+            if (cls[t] >= n_classes) return fail(h, COV_ERR_INVALID, "cov_set_grid_cells: class index out of range");
+    h->have_grid = false;
+    describe_lattice(h, nx, ny, dx, dy);
+    OK(alloc_cells(h));
+    CK(cudaMemcpyAsync(h->mult.p, mult, ncell, cudaMemcpyHostToDevice, h->stream));
+    if (cls) CK(cudaMemcpyAsync(h->cls.p, cls, ncell, cudaMemcpyHostToDevice, h->stream));
+    else CK(cudaMemsetAsync(h->cls.p, 0, ncell, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return rebuild_planes(h, (int)n_classes, class_weight);
+}
+
+extern "C" int cov_set_grid_full(cov_handle *h, int64_t nx, int64_t ny, double dx, double dy)
+{
+    if (!h) return fail(nullptr, COV_ERR_INVALID, "NULL handle");
+    DeviceGuard dg(h->device);
+    OK(check_lattice(h, nx, ny, dx, dy));
+    h->have_grid = false;
+    describe_lattice(h, nx, ny, dx, dy);
+    OK(alloc_cells(h));
+    CK(launch_fill_full((unsigned char *)h->mult.p, (unsigned char *)h->cls.p, (long long)nx * ny, h->stream));
+    h->launches += 1;
+    const double w = dx * dy; // createPOI: area = weight = dx*dy
+    return rebuild_planes(h, 1, &w);
+}
+
+// Map list entries onto the lattice (bit-exact centre check) and weight classes.
+static int map_points(cov_handle *h, const double *pts5, int64_t P, std::vector<int> &cell,
+                      std::vector<unsigned char> &pcls, int &n_classes, double *class_weight)
+{
+    const GridDesc &g = h->g;
+    cell.resize((size_t)P);
+    pcls.resize((size_t)P);
+    for (int64_t p = 0; p < P; ++p) {
+        const double x = pts5[5 * p], y = pts5[5 * p + 1], w = pts5[5 * p + 3];
+        const double fi = std::nearbyint((x + g.hdx) / g.dx), fj = std::nearbyint((y + g.hdy) / g.dy);
+        bool ok = fi >= 1 && fi <= g.nx && fj >= 1 && fj <= g.ny;
+        if (ok) {
+            volatile double cx = fi * g.dx; // individually rounded, as the reference forms them
+            volatile double cy = fj * g.dy;
+            ok = (cx - g.hdx == x) && (cy - g.hdy == y);
+        }
+        if (!ok) {
+            char buf[160];
+            snprintf(buf, sizeof buf, "point %lld (%.17g, %.17g) is not a cell centre of the %dx%d lattice",
+                     (long long)p, x, y, g.nx, g.ny);
+            return fail(h, COV_ERR_OFF_LATTICE, buf);
+        }
+        int k = -1;
+        for (int q = 0; q < n_classes; ++q)
+            if (class_weight[q] == w) {
+                k = q;
+                break;
+            }
+        if (k < 0) {
+            if (w != w) return fail(h, COV_ERR_INVALID, "point weight is NaN");
+            if (n_classes >= kMaxClasses)
+                return fail(h, COV_ERR_LIMIT, "more than 4 distinct point weights");
+            k = n_classes;
+            class_weight[n_classes++] = w;
+        }
+        cell[(size_t)p] = ((int)fi - 1) + g.nx * ((int)fj - 1);
+        pcls[(size_t)p] = (unsigned char)k;
+    }
+    return COV_OK;
+}
+
+static int upload_points(cov_handle *h, const std::vector<int> &cell, const std::vector<unsigned char> &pcls)
+{
+    const size_t P = cell.size();
+    if (P == 0) return COV_OK;
+    DevBuf dcell, dcls;
+    int rc = ensure(h, dcell, P * sizeof(int));
+    if (rc == COV_OK) rc = ensure(h, dcls, P);
+    cudaError_t e = cudaSuccess;
+    int *hov = (int *)h->h_small;
+    if (rc == COV_OK) {
+        e = cudaMemcpyAsync(dcell.p, cell.data(), P * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dcls.p, pcls.data(), P, cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(h->overflow.p, 0, sizeof(int), h->stream);
+        if (e == cudaSuccess)
+            e = launch_add_points((unsigned char *)h->mult.p, (unsigned char *)h->cls.p, (const int *)dcell.p,
+                                  (const unsigned char *)dcls.p, (long long)P, (int *)h->overflow.p, h->stream);
+        h->launches += 1;
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(hov, h->overflow.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    }
+    if (dcell.p) cudaFree(dcell.p);
+    if (dcls.p) cudaFree(dcls.p);
+    if (rc != COV_OK) return rc;
+    if (e != cudaSuccess) return fail_cuda(h, e, "upload_points");
+    if (*hov == 1) return fail(h, COV_ERR_LIMIT, "more than 255 list entries on one cell");
+    if (*hov == 2) return fail(h, COV_ERR_INVALID, "entries on one cell carry different weights");
+    return COV_OK;
+}
+
+extern "C" int cov_set_points(cov_handle *h, const double *pts5, int64_t P, int64_t nx, int64_t ny, double dx,
+                              double dy)
+{
+    if (!h) return fail(nullptr, COV_ERR_INVALID, "NULL handle");
+    DeviceGuard dg(h->device);
+    if (P < 0 || (P > 0 && !pts5)) return fail(h, COV_ERR_INVALID, "cov_set_points: bad list");
+    OK(check_lattice(h, nx, ny, dx, dy));
+    h->have_grid = false;
+    describe_lattice(h, nx, ny, dx, dy);
+    std::vector<int> cell;
+    std::vector<unsigned char> pcls;
+    int n_classes = 0;
+    double cw[kMaxClasses] = {0, 0, 0, 0};
+    OK(map_points(h, pts5, P, cell, pcls, n_classes, cw));
+    if (n_classes == 0) {
+        n_classes = 1;
+        cw[0] = dx * dy;
+    }
+    OK(alloc_cells(h));
+    const size_t ncell = (size_t)nx * ny;
+    CK(cudaMemsetAsync(h->mult.p, 0, ncell + 4, h->stream));
+    CK(cudaMemsetAsync(h->cls.p, 0, ncell + 4, h->stream));
+    OK(upload_points(h, cell, pcls));
+    return rebuild_planes(h, n_classes, cw);
+}
+
+extern "C" int cov_add_points(cov_handle *h, const double *pts5, int64_t P)
+{
+    if (!h) return fail(nullptr, COV_ERR_INVALID, "NULL handle");
+    DeviceGuard dg(h->device);
+    if (!h->have_grid) return fail(h, COV_ERR_STATE, "cov_add_points: no grid set");
+    if (P < 0 || (P > 0 && !pts5)) return fail(h, COV_ERR_INVALID, "cov_add_points: bad list");
+    std::vector<int> cell;
+    std::vector<unsigned char> pcls;
+    int n_classes = h->g.n_classes;
+    double cw[kMaxClasses];
+    for (int k = 0; k < kMaxClasses; ++k) cw[k] = h->g.class_weight[k];
+    if (h->n_entries == 0) n_classes = 0; // an empty store has no weight yet
+    OK(map_points(h, pts5, P, cell, pcls, n_classes, cw));
+    if (n_classes == 0) {
+        n_classes = 1;
+        cw[0] = h->g.class_weight[0];
+    }
+    OK(upload_points(h, cell, pcls));
+    return rebuild_planes(h, n_classes, cw);
+}
+
+extern "C" int cov_get_grid_info(const cov_handle *h, cov_grid_info *info)
+{
+    if (!h || !info) return COV_ERR_INVALID;
+    if (!h->have_grid) return COV_ERR_STATE;
+    info->nx = h->g.nx;
+    info->ny = h->g.ny;
+    info->dx = h->g.dx;
+    info->dy = h->g.dy;
+    info->n_entries = h->n_entries;
+    info->n_cells = h->n_cells;
+    info->n_planes = h->g.n_planes;
+    info->n_classes = h->g.n_classes;
+    info->area_exact = h->area_exact;
+    info->planes_in_smem = span_planes_fit_smem(h->g, h->have_params ? h->o.N : 1, h->cfg);
+    return COV_OK;
+}
+
+extern "C" int cov_get_grid_cells(cov_handle *h, uint8_t *mult)
+{
+    if (!h) return fail(nullptr, COV_ERR_INVALID, "NULL handle");
+    DeviceGuard dg(h->device);
+    if (!h->have_grid) return fail(h, COV_ERR_STATE, "no grid set");
+    if (!mult) return fail(h, COV_ERR_INVALID, "NULL output");
+    CK(cudaMemcpyAsync(mult, h->mult.p, (size_t)h->g.nx * h->g.ny, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return COV_OK;
+}
+
+// discs [x;y;R] -> device [x;y;T(R)]
+static int upload_discs_T(cov_handle *h, const double *xyR, int64_t N)
+{
+    if (N < 1 || N > kMaxUavs) return fail(h, COV_ERR_LIMIT, "N must be 1..1024");
+    if (!xyR) return fail(h, COV_ERR_INVALID, "NULL disc vector");
+    OK(ensure(h, h->xyT, (size_t)3 * N * 8));
+    OK(ensure(h, h->small_in, (size_t)3 * N * 8));
+    CK(cudaMemcpyAsync(h->small_in.p, xyR, (size_t)3 * N * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(launch_thresholds((const double *)h->small_in.p, (int)N, (double *)h->xyT.p, h->stream));
+    h->launches += 1;
+    return COV_OK;
+}
+
+extern "C" int cov_remove_covered(cov_handle *h, const double *xyR, int64_t N, int64_t *removed)
+{
+    if (!h) return fail(nullptr, COV_ERR_INVALID, "NULL handle");
+    DeviceGuard dg(h->device);
+    if (!h->have_grid) return fail(h, COV_ERR_STATE, "cov_remove_covered: no grid set");
+    OK(upload_discs_T(h, xyR, N));
+    CK(launch_remove_covered((unsigned char *)h->mult.p, h->g, (const double *)h->xyT.p, (int)N,
+                             (unsigned long long *)h->removed.p, h->stream));
+    h->launches += 1;
+    unsigned long long *hr = (unsigned long long *)h->h_small + 16;
+    CK(cudaMemcpyAsync(hr, h->removed.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (removed) *removed = (int64_t)*hr;
+    double cw[kMaxClasses];
+    for (int k = 0; k < kMaxClasses; ++k) cw[k] = h->g.class_weight[k];
+    return rebuild_planes(h, h->g.n_classes, cw);
+}
+
+extern "C" int cov_covered_mask(cov_handle *h, const double *x, uint8_t *mask)
+{
+    if (!h) return fail(nullptr, COV_ERR_INVALID, "NULL handle");
+    DeviceGuard dg(h->device);
+    if (!h->have_grid || !h->have_params) return fail(h, COV_ERR_STATE, "cov_covered_mask: grid/params not set");
+    if (!mask) return fail(h, COV_ERR_INVALID, "NULL output");
+    OK(upload_discs_T(h, x, h->o.N));
+    const size_t ncell = (size_t)h->g.nx * h->g.ny;
+    DevBuf dm;
+    OK(ensure(h, dm, ncell));
+    cudaError_t e = launch_covered_mask((unsigned char *)dm.p, h->g, (const double *)h->xyT.p, h->o.N, h->stream);
+    h->launches += 1;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(mask, dm.p, ncell, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(dm.p);
+    if (e != cudaSuccess) return fail_cuda(h, e, "cov_covered_mask");
+    return COV_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// parameters
+// ------------------------------------------------------------------------------------------
+extern "C" int cov_set_params(cov_handle *h, int64_t N, const double *r_max, double penalty_scale,
+                              const double *prev_xyR, const double *d_lim, double tan_half_fov, double sep_min,
+                              int32_t use_cons7)
+{
+    if (!h) return fail(nullptr, COV_ERR_INVALID, "NULL handle");
+    DeviceGuard dg(h->device);
+    if (N < 1 || N > kMaxUavs) return fail(h, COV_ERR_LIMIT, "cov_set_params: N must be 1..1024");
+    if (!r_max) return fail(h, COV_ERR_INVALID, "cov_set_params: r_max is NULL");
+    if (prev_xyR && !d_lim) return fail(h, COV_ERR_INVALID, "cov_set_params: d_lim is NULL while prev_xyR is set");
+    std::vector<double> hp((size_t)5 * N, 0.0);
+    for (int64_t i = 0; i < N; ++i) hp[i] = r_max[i];
+    if (prev_xyR)
+        for (int64_t i = 0; i < N; ++i) {
+            hp[N + i] = prev_xyR[i];
+            hp[2 * N + i] = prev_xyR[N + i];
+            volatile double z = prev_xyR[2 * N + i] / tan_half_fov; // z1 = pre.R / tan(FOV/2)
+            hp[3 * N + i] = z;
+            hp[4 * N + i] = threshold_ge(d_lim[i]);
+        }
+    OK(ensure(h, h->params, (size_t)5 * N * 8));
+    // pageable source: the copy is staged before the call returns, hp may go out of scope
+    CK(cudaMemcpyAsync(h->params.p, hp.data(), (size_t)5 * N * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    ObjParams &o = h->o;
+    o.N = (int)N;
+    o.use_cons3 = prev_xyR != nullptr;
+    o.use_cons7 = use_cons7 != 0;
+    o.use_cons8 = sep_min > 0;
+    o.penalty_scale = penalty_scale;
+    o.tan_half_fov = tan_half_fov;
+    {
+        volatile double c7 = 19 * tan_half_fov;
+        o.cons7_R = c7;
+    }
+    o.sep_T = o.use_cons8 ? threshold(sep_min) : 0.0;
+    const double *base = (const double *)h->params.p;
+    o.r_max = base;
+    o.prev_x = base + N;
+    o.prev_y = base + 2 * N;
+    o.prev_z = base + 3 * N;
+    o.cons3_G = base + 4 * N;
+    h->have_params = true;
+    return COV_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// evaluation
+// ------------------------------------------------------------------------------------------
+static int launch_on_main(cov_handle *h, const double *dX, int64_t B, const EvalOut &out, bool timed)
+{
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (timed) {
+        e0 = get_event(h);
+        e1 = get_event(h);
+        CK(cudaEventRecord(e0, h->stream));
+    }
+    cudaError_t e = launch_eval(h->g, h->o, h->cfg, dX, (long long)B, out, (unsigned long long *)h->counter.p,
+                                h->stream, &h->last_info);
+    if (e != cudaSuccess) {
+        if (timed) {
+            h->ev_pool.push_back(e0);
+            h->ev_pool.push_back(e1);
+        }
+        if (e == cudaErrorInvalidConfiguration) {
+            (void)cudaGetLastError();
+            return fail(h, COV_ERR_LIMIT, "grid row / N too large for the shared-memory plan of this kernel");
+        }
+        return fail_cuda(h, e, "coverage kernel launch");
+    }
+    h->launches += 1;
+    if (timed) {
+        CK(cudaEventRecord(e1, h->stream));
+        h->kernel_spans.emplace_back(e0, e1);
+    }
+    return COV_OK;
+}
+
+static int check_ready(cov_handle *h, const char *who)
+{
+    if (!h->have_grid) return fail(h, COV_ERR_STATE, std::string(who) + ": no grid set");
+    if (!h->have_params) return fail(h, COV_ERR_STATE, std::string(who) + ": no parameters set");
+    return COV_OK;
+}
+
+extern "C" int cov_eval_batch_device(cov_handle *h, const double *dX, int64_t B, double *d_obj, int64_t *d_count,
+                                     uint8_t *d_feasible)
+{
+    if (!h) return fail(nullptr, COV_ERR_INVALID, "NULL handle");
+    DeviceGuard dg(h->device);
+    OK(check_ready(h, "cov_eval_batch_device"));
+    if (B < 0 || (B > 0 && (!dX || !d_obj))) return fail(h, COV_ERR_INVALID, "cov_eval_batch_device: bad arguments");
+    if (B == 0) return COV_OK;
+    recycle_spans(h);
+    EvalOut out{};
+    out.obj = d_obj;
+    out.count = (long long *)d_count;
+    out.feasible = d_feasible;
+    return launch_on_main(h, dX, B, out, true);
+}
+
+// The host pipeline: candidates are cut into slices; slice k's H2D copy (stream s_in), the kernel
+// of slice k-1 (main stream) and the D2H copy of slice k-2's results (stream s_out) overlap.
+// Pageable host buffers go through two pinned staging buffers; pinned ones are DMA'd in place.
+static int eval_host(cov_handle *h, const double *X, int64_t B, double *obj, int64_t *count, uint8_t *feasible,
+                     int64_t *class_count, double *progressive)
+{
+    OK(check_ready(h, "cov_eval_batch"));
+    if (B < 0 || (B > 0 && (!X || !obj))) return fail(h, COV_ERR_INVALID, "cov_eval_batch: bad arguments");
+    if (B == 0) return COV_OK;
+    recycle_spans(h);
+    const int N = h->o.N;
+    const int ncls = h->g.n_classes;
+    const size_t row_bytes = (size_t)3 * N * 8;
+    // device window: at most ~1 GiB of candidates at a time
+    const int64_t window = std::max<int64_t>(1, std::min<int64_t>(B, (int64_t)((1ull << 30) / row_bytes)));
+    int64_t chunk = h->chunk > 0 ? h->chunk : std::max<int64_t>(1024, (int64_t)((16ull << 20) / row_bytes));
+    chunk = std::min(chunk, window);
+    OK(ensure(h, h->dX, (size_t)window * row_bytes));
+    OK(ensure(h, h->d_obj, (size_t)window * 8));
+    if (count) OK(ensure(h, h->d_count, (size_t)window * 8));
+    if (feasible) OK(ensure(h, h->d_feas, (size_t)window));
+    if (class_count) OK(ensure(h, h->d_clscnt, (size_t)window * 8 * ncls));
+    if (progressive) OK(ensure(h, h->d_prog, (size_t)window * 8));
+    const bool in_pinned = is_pinned_host(X);
+    if (!in_pinned)
+        for (int k = 0; k < 2; ++k) {
+            size_t cap = h->h_in_cap;
+            OK(ensure_pinned(h, &h->h_in[k], &cap, (size_t)chunk * row_bytes));
+            if (k == 1) h->h_in_cap = cap;
+        }
+    // outputs that are not pinned are staged per window and copied out at the window's end
+    const bool obj_p = is_pinned_host(obj), cnt_p = !count || is_pinned_host(count),
+               fea_p = !feasible || is_pinned_host(feasible), cls_p = !class_count || is_pinned_host(class_count),
+               prg_p = !progressive || is_pinned_host(progressive);
+    size_t stage_out = 0;
+    size_t off_obj = 0, off_cnt = 0, off_fea = 0, off_cls = 0, off_prg = 0;
+    if (!obj_p) { off_obj = stage_out; stage_out += (size_t)window * 8; }
+    if (!cnt_p) { off_cnt = stage_out; stage_out += (size_t)window * 8; }
+    if (!cls_p) { off_cls = stage_out; stage_out += (size_t)window * 8 * ncls; }
+    if (!prg_p) { off_prg = stage_out; stage_out += (size_t)window * 8; }
+    if (!fea_p) { off_fea = stage_out; stage_out += (size_t)window; }
+    if (stage_out) OK(ensure_pinned(h, &h->h_out, &h->h_out_cap, stage_out));
+    char *so = (char *)h->h_out;
+
+    cudaEvent_t ev_in = get_event(h), ev_k = get_event(h), ev_free[2] = {get_event(h), get_event(h)};
+    bool free_armed[2] = {false, false};
+    int rc = COV_OK;
+    auto done = [&](int code) {
+        h->ev_pool.push_back(ev_in);
+        h->ev_pool.push_back(ev_k);
+        h->ev_pool.push_back(ev_free[0]);
+        h->ev_pool.push_back(ev_free[1]);
+        return code;
+    };
+#define CKD(call)                                                         \
+    do {                                                                  \
+        cudaError_t e_ = (call);                                          \
+        if (e_ != cudaSuccess) return done(fail_cuda(h, e_, #call));      \
+    } while (0)
+    // the copy streams must not start before earlier work on the main stream (grid/params) is done
+    CKD(cudaEventRecord(ev_k, h->stream));
+    CKD(cudaStreamWaitEvent(h->s_in, ev_k, 0));
+    for (int64_t w0 = 0; w0 < B; w0 += window) {
+        const int64_t wn = std::min(window, B - w0);
+        int slot = 0;
+        for (int64_t c0 = 0; c0 < wn; c0 += chunk, slot ^= 1) {
+            const int64_t cn = std::min(chunk, wn - c0);
+            const double *src = X + (size_t)(w0 + c0) * 3 * N;
+            double *dst = (double *)h->dX.p + (size_t)c0 * 3 * N;
+            if (!in_pinned) {
+                if (free_armed[slot]) CKD(cudaEventSynchronize(ev_free[slot]));
+                memcpy(h->h_in[slot], src, (size_t)cn * row_bytes);
+                src = (const double *)h->h_in[slot];
+            }
+            CKD(cudaMemcpyAsync(dst, src, (size_t)cn * row_bytes, cudaMemcpyHostToDevice, h->s_in));
+            if (!in_pinned) {
+                CKD(cudaEventRecord(ev_free[slot], h->s_in));
+                free_armed[slot] = true;
+            }
+            CKD(cudaEventRecord(ev_in, h->s_in));
+            CKD(cudaStreamWaitEvent(h->stream, ev_in, 0));
+            EvalOut out{};
+            out.obj = (double *)h->d_obj.p + c0;
+            out.count = count ? (long long *)h->d_count.p + c0 : nullptr;
+            out.feasible = feasible ? (unsigned char *)h->d_feas.p + c0 : nullptr;
+            out.class_count = class_count ? (long long *)h->d_clscnt.p + (size_t)c0 * ncls : nullptr;
+            out.progressive = progressive ? (double *)h->d_prog.p + c0 : nullptr;
+            rc = launch_on_main(h, dst, cn, out, true);
+            if (rc != COV_OK) return done(rc);
+            CKD(cudaEventRecord(ev_k, h->stream));
+            CKD(cudaStreamWaitEvent(h->s_out, ev_k, 0));
+            const int64_t g0 = w0 + c0;
+            CKD(cudaMemcpyAsync(obj_p ? (void *)(obj + g0) : (void *)(so + off_obj + (size_t)c0 * 8), out.obj,
+                                (size_t)cn * 8, cudaMemcpyDeviceToHost, h->s_out));
+            if (count)
+                CKD(cudaMemcpyAsync(cnt_p ? (void *)(count + g0) : (void *)(so + off_cnt + (size_t)c0 * 8),
+                                    out.count, (size_t)cn * 8, cudaMemcpyDeviceToHost, h->s_out));
+            if (feasible)
+                CKD(cudaMemcpyAsync(fea_p ? (void *)(feasible + g0) : (void *)(so + off_fea + (size_t)c0),
+                                    out.feasible, (size_t)cn, cudaMemcpyDeviceToHost, h->s_out));
+            if (class_count)
+                CKD(cudaMemcpyAsync(cls_p ? (void *)(class_count + (size_t)g0 * ncls)
+                                          : (void *)(so + off_cls + (size_t)c0 * 8 * ncls),
+                                    out.class_count, (size_t)cn * 8 * ncls, cudaMemcpyDeviceToHost, h->s_out));
+            if (progressive)
+                CKD(cudaMemcpyAsync(prg_p ? (void *)(progressive + g0) : (void *)(so + off_prg + (size_t)c0 * 8),
+                                    out.progressive, (size_t)cn * 8, cudaMemcpyDeviceToHost, h->s_out));
+        }
+        // end of window: results home, device window reusable
+        CKD(cudaStreamSynchronize(h->s_out));
+        if (!obj_p) memcpy(obj + w0, so + off_obj, (size_t)wn * 8);
+        if (!cnt_p) memcpy(count + w0, so + off_cnt, (size_t)wn * 8);
+        if (!fea_p) memcpy(feasible + w0, so + off_fea, (size_t)wn);
+        if (!cls_p) memcpy(class_count + (size_t)w0 * ncls, so + off_cls, (size_t)wn * 8 * ncls);
+        if (!prg_p) memcpy(progressive + w0, so + off_prg, (size_t)wn * 8);
+    }
+#undef CKD
+    return done(COV_OK);
+}
+
+extern "C" int cov_eval_batch(cov_handle *h, const double *X, int64_t B, double *obj, int64_t *count,
+                              uint8_t *feasible)
+{
+    if (!h) return fail(nullptr, COV_ERR_INVALID, "NULL handle");
+    DeviceGuard dg(h->device);
+    return eval_host(h, X, B, obj, count, feasible, nullptr, nullptr);
+}
+
+extern "C" int cov_eval_batch_ex(cov_handle *h, const double *X, int64_t B, double *obj, int64_t *count,
+                                 uint8_t *feasible, int64_t *class_count, double *progressive)
+{
+    if (!h) return fail(nullptr, COV_ERR_INVALID, "NULL handle");
+    DeviceGuard dg(h->device);
+    return eval_host(h, X, B, obj, count, feasible, class_count, progressive);
+}
+
+// One candidate through pinned scratch: copy in, one launch, copy out, one synchronisation.
+extern "C" int cov_eval_one(cov_handle *h, const double *x, double *obj)
+{
+    if (!h) return fail(nullptr, COV_ERR_INVALID, "NULL handle");
+    DeviceGuard dg(h->device);
+    OK(check_ready(h, "cov_eval_one"));
+    if (!x || !obj) return fail(h, COV_ERR_INVALID, "cov_eval_one: NULL argument");
+    recycle_spans(h);
+    const int N = h->o.N;
+    const size_t bytes = (size_t)3 * N * 8;
+    char *hx = (char *)h->h_small + 4096; // pinned scratch for one candidate (3 * kMaxUavs doubles)
+    OK(ensure(h, h->dX, bytes));
+    OK(ensure(h, h->d_obj, 8));
+    memcpy(hx, x, bytes);
+    CK(cudaMemcpyAsync(h->dX.p, hx, bytes, cudaMemcpyHostToDevice, h->stream));
+    EvalOut out{};
+    out.obj = (double *)h->d_obj.p;
+    OK(launch_on_main(h, (const double *)h->dX.p, 1, out, false));
+    double *hres = (double *)h->h_small + 32;
+    CK(cudaMemcpyAsync(hres, h->d_obj.p, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *obj = *hres;
+    return COV_OK;
+}
+
+extern "C" int cov_argmin(cov_handle *h, const double *X, int64_t B, int32_t barrier, double *best_obj,
+                          int64_t *best_idx)
+{
+    if (!h) return fail(nullptr, COV_ERR_INVALID, "NULL handle");
+    DeviceGuard dg(h->device);
+    OK(check_ready(h, "cov_argmin"));
+    if (B < 0 || (B > 0 && !X) || !best_obj || !best_idx) return fail(h, COV_ERR_INVALID, "cov_argmin: bad arguments");
+    double best = INFINITY;
+    int64_t bidx = -1;
+    recycle_spans(h);
+    const int N = h->o.N;
+    const size_t row_bytes = (size_t)3 * N * 8;
+    const int64_t window = std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(B, 1), (int64_t)((1ull << 30) / row_bytes)));
+    OK(ensure(h, h->dX, (size_t)window * row_bytes));
+    OK(ensure(h, h->d_obj, (size_t)window * 8));
+    OK(ensure(h, h->d_feas, (size_t)window));
+    for (int64_t w0 = 0; w0 < B; w0 += window) {
+        const int64_t wn = std::min(window, B - w0);
+        CK(cudaMemcpyAsync(h->dX.p, X + (size_t)w0 * 3 * N, (size_t)wn * row_bytes, cudaMemcpyHostToDevice, h->stream));
+        EvalOut out{};
+        out.obj = (double *)h->d_obj.p;
+        out.feasible = (unsigned char *)h->d_feas.p;
+        OK(launch_on_main(h, (const double *)h->dX.p, wn, out, true));
+        CK(launch_argmin(out.obj, out.feasible, wn, barrier, (double *)h->argmin_obj.p, (long long *)h->argmin_idx.p,
+                         1024, h->stream));
+        h->launches += 2;
+        double *ho = (double *)h->h_small + 40;
+        long long *hi = (long long *)h->h_small + 41;
+        CK(cudaMemcpyAsync(ho, h->argmin_obj.p, 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(hi, h->argmin_idx.p, 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (*hi >= 0 && (bidx < 0 || *ho < best)) { // ties keep the earlier window's index
+            best = *ho;
+            bidx = w0 + *hi;
+        }
+    }
+    *best_obj = bidx >= 0 ? best : INFINITY;
+    *best_idx = bidx;
+    return COV_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// streams, memory, timing
+// ------------------------------------------------------------------------------------------
+extern "C" int cov_sync(cov_handle *h)
+{
+    if (!h) return fail(nullptr, COV_ERR_INVALID, "NULL handle");
+    DeviceGuard dg(h->device);
+    CK(cudaStreamSynchronize(h->s_in));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaStreamSynchronize(h->s_out));
+    return COV_OK;
+}
+extern "C" void *cov_stream(cov_handle *h) { return h ? (void *)h->stream : nullptr; }
+extern "C" int cov_set_stream(cov_handle *h, void *stream)
+{
+    if (!h) return fail(nullptr, COV_ERR_INVALID, "NULL handle");
+    DeviceGuard dg(h->device);
+    CK(cudaStreamSynchronize(h->stream));
+    h->stream = stream ? (cudaStream_t)stream : h->own_stream;
+    return COV_OK;
+}
+extern "C" int cov_host_alloc(cov_handle *h, int64_t bytes, void **out)
+{
+    if (!h || !out || bytes < 0) return fail(h, COV_ERR_INVALID, "cov_host_alloc: bad arguments");
+    DeviceGuard dg(h->device);
+    *out = nullptr;
+    cudaError_t e = cudaMallocHost(out, (size_t)std::max<int64_t>(bytes, 1));
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(h, COV_ERR_NOMEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+    }
+    return COV_OK;
+}
+extern "C" int cov_host_free(cov_handle *h, void *p)
+{
+    if (!h) return fail(nullptr, COV_ERR_INVALID, "NULL handle");
+    DeviceGuard dg(h->device);
+    if (p) CK(cudaFreeHost(p));
+    return COV_OK;
+}
+extern "C" int cov_device_alloc(cov_handle *h, int64_t bytes, void **out)
+{
+    if (!h || !out || bytes < 0) return fail(h, COV_ERR_INVALID, "cov_device_alloc: bad arguments");
+    DeviceGuard dg(h->device);
+    *out = nullptr;
+    cudaError_t e = cudaMalloc(out, (size_t)std::max<int64_t>(bytes, 1));
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(h, COV_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    }
+    return COV_OK;
+}
+extern "C" int cov_device_free(cov_handle *h, void *p)
+{
+    if (!h) return fail(nullptr, COV_ERR_INVALID, "NULL handle");
+    DeviceGuard dg(h->device);
+    if (p) CK(cudaFree(p));
+    return COV_OK;
+}
+extern "C" int cov_memcpy_h2d(cov_handle *h, void *dst, const void *src, int64_t bytes)
+{
+    if (!h || bytes < 0) return fail(h, COV_ERR_INVALID, "cov_memcpy_h2d: bad arguments");
+    DeviceGuard dg(h->device);
+    CK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, h->stream));
+    return COV_OK;
+}
+extern "C" int cov_memcpy_d2h(cov_handle *h, void *dst, const void *src, int64_t bytes)
+{
+    if (!h || bytes < 0) return fail(h, COV_ERR_INVALID, "cov_memcpy_d2h: bad arguments");
+    DeviceGuard dg(h->device);
+    CK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, h->stream));
+    return COV_OK;
+}
+extern "C" int64_t cov_launch_count(const cov_handle *h) { return h ? h->launches : 0; }
+
+extern "C" int cov_last_kernel_ms(cov_handle *h, double *ms)
+{
+    if (!h || !ms) return fail(h, COV_ERR_INVALID, "cov_last_kernel_ms: bad arguments");
+    DeviceGuard dg(h->device);
+    if (h->last_call_ms_cache < 0 || h->kernel_spans.size() > h->last_call_begin) {
+        const double before = h->last_call_ms_cache < 0 ? 0 : h->last_call_ms_cache;
+        CK(drain_spans(h));
+        h->last_call_ms_cache += before;
+    }
+    *ms = h->last_call_ms_cache;
+    return COV_OK;
+}
+
+extern "C" int cov_kernel_time_total(cov_handle *h, double *ms, int64_t *launches)
+{
+    if (!h) return fail(nullptr, COV_ERR_INVALID, "NULL handle");
+    DeviceGuard dg(h->device);
+    const double keep = h->last_call_ms_cache;
+    const bool pending = h->kernel_spans.size() > h->last_call_begin;
+    CK(drain_spans(h));
+    if (keep >= 0 && pending) h->last_call_ms_cache += keep;
+    else if (keep >= 0 && !pending) h->last_call_ms_cache = keep;
+    if (ms) *ms = h->drained_ms;
+    if (launches) *launches = h->drained_launches;
+    return COV_OK;
+}
+
+extern "C" int cov_generate_candidates(cov_handle *h, double *dX, int64_t B, int64_t N, uint64_t seed,
+                                       int64_t first_index, double lx, double ly, double h_min, double h_max,
+                                       double tan_half_fov)
+{
+    if (!h) return fail(nullptr, COV_ERR_INVALID, "NULL handle");
+    DeviceGuard dg(h->device);
+    if (B < 0 || N < 1 || N > kMaxUavs || (B > 0 && !dX)) return fail(h, COV_ERR_INVALID, "cov_generate_candidates: bad arguments");
+    CK(launch_generate(dX, (long long)B, (int)N, seed, (long long)first_index, lx, ly, h_min, h_max, tan_half_fov,
+                       h->stream));
+    h->launches += 1;
+    return COV_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// several GPUs of one box: contiguous candidate slices, one host thread per device
+// ------------------------------------------------------------------------------------------
+struct cov_multi {
+    std::vector<cov_handle *> hs;
+    std::string err;
+};
+
+extern "C" int cov_multi_create(const int *devices, int n, cov_multi **out)
+{
+    if (!out || n < 1 || !devices) return fail(nullptr, COV_ERR_INVALID, "cov_multi_create: bad arguments");
+    *out = nullptr;
+    cov_multi *m = new cov_multi();
+    for (int k = 0; k < n; ++k) {
+        cov_handle *h = nullptr;
+        int rc = cov_create(devices[k], &h);
+        if (rc != COV_OK) {
+            for (cov_handle *q : m->hs) cov_destroy(q);
+            delete m;
+            return rc;
+        }
+        m->hs.push_back(h);
+    }
+    *out = m;
+    return COV_OK;
+}
+extern "C" void cov_multi_destroy(cov_multi *m)
+{
+    if (!m) return;
+    for (cov_handle *h : m->hs) cov_destroy(h);
+    delete m;
+}
+extern "C" const char *cov_multi_last_error(const cov_multi *m) { return m ? m->err.c_str() : g_err_nohandle.c_str(); }
+extern "C" int cov_multi_size(const cov_multi *m) { return m ? (int)m->hs.size() : 0; }
+extern "C" cov_handle *cov_multi_handle(cov_multi *m, int k)
+{
+    return (m && k >= 0 && k < (int)m->hs.size()) ? m->hs[k] : nullptr;
+}
+
+static void shard(int64_t B, int G, int k, int64_t &b0, int64_t &bn)
+{
+    const int64_t per = (B + G - 1) / G; // ceil(B/G), SURVEY.md 8e
+    b0 = std::min<int64_t>(B, per * k);
+    bn = std::min<int64_t>(B, b0 + per) - b0;
+}
+
+extern "C" int cov_multi_eval_batch(cov_multi *m, const double *X, int64_t B, double *obj, int64_t *count,
+                                    uint8_t *feasible)
+{
+    if (!m) return fail(nullptr, COV_ERR_INVALID, "NULL multi handle");
+    if (B < 0 || (B > 0 && (!X || !obj))) {
+        m->err = "cov_multi_eval_batch: bad arguments";
+        return COV_ERR_INVALID;
+    }
+    const int G = (int)m->hs.size();
+    std::vector<int> rcs((size_t)G, COV_OK);
+    std::vector<std::thread> th;
+    for (int k = 0; k < G; ++k)
+        th.emplace_back([&, k]() {
+            int64_t b0, bn;
+            shard(B, G, k, b0, bn);
+            if (bn <= 0) return;
+            cov_handle *h = m->hs[k];
+            const int N = h->have_params ? h->o.N : 0;
+            rcs[k] = cov_eval_batch(h, X + (size_t)b0 * 3 * N, bn, obj + b0, count ? count + b0 : nullptr,
+                                    feasible ? feasible + b0 : nullptr);
+        });
+    for (auto &t : th) t.join();
+    for (int k = 0; k < G; ++k)
+        if (rcs[k] != COV_OK) {
+            m->err = "device shard " + std::to_string(k) + ": " + m->hs[k]->err;
+            return rcs[k];
+        }
+    return COV_OK;
+}
+
+extern "C" int cov_multi_argmin(cov_multi *m, const double *X, int64_t B, int32_t barrier, double *best_obj,
+                                int64_t *best_idx)
+{
+    if (!m) return fail(nullptr, COV_ERR_INVALID, "NULL multi handle");
+    if (B < 0 || (B > 0 && !X) || !best_obj || !best_idx) {
+        m->err = "cov_multi_argmin: bad arguments";
+        return COV_ERR_INVALID;
+    }
+    const int G = (int)m->hs.size();
+    std::vector<int> rcs((size_t)G, COV_OK);
+    std::vector<double> bo((size_t)G, INFINITY);
+    std::vector<int64_t> bi((size_t)G, -1);
+    std::vector<std::thread> th;
+    for (int k = 0; k < G; ++k)
+        th.emplace_back([&, k]() {
+            int64_t b0, bn;
+            shard(B, G, k, b0, bn);
+            if (bn <= 0) return;
+            cov_handle *h = m->hs[k];
+            const int N = h->have_params ? h->o.N : 0;
+            rcs[k] = cov_argmin(h, X + (size_t)b0 * 3 * N, bn, barrier, &bo[k], &bi[k]);
+            if (rcs[k] == COV_OK && bi[k] >= 0) bi[k] += b0;
+        });
+    for (auto &t : th) t.join();
+    double best = INFINITY;
+    int64_t idx = -1;
+    for (int k = 0; k < G; ++k) {
+        if (rcs[k] != COV_OK) {
+            m->err = "device shard " + std::to_string(k) + ": " + m->hs[k]->err;
+            return rcs[k];
+        }
+        if (bi[k] >= 0 && (idx < 0 || bo[k] < best)) { // 16-byte (min, index) pair per GPU, host gather
+            best = bo[k];
+            idx = bi[k];
+        }
+    }
+    *best_obj = best;
+    *best_idx = idx;
+    return COV_OK;
+}

@@ -1,0 +1,398 @@
+// cov_grid_kernels.cu -- device-side cell store of libcoverage_cuda and the small utility kernels
+// around the objective (all citations relative to /root/reference/):
+//   cell store         CellFunctions.Cells.points_of_interest        src/CellFunctions.jl:5-16
+//   fill_full          createPOI                                      src/AreaCoverageCalculation.jl:11-21
+//   add_points         update_POI's push!                             src/CellFunctions.jl:59-79
+//   remove_covered     rmvCoveredPOI                                  src/CellFunctions.jl:81-108
+// The canonical store is one multiplicity byte and one class byte per cell; the bit planes the
+// objective kernels sweep are derived from it by pack_planes.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdint>
+#include "cov_device.cuh"
+#include "cov_kernels.cuh"
+
+namespace cov {
+
+__global__ void grid_stats_kernel(const unsigned char *__restrict__ mult, const unsigned char *__restrict__ cls,
+                                  long long ncell, unsigned long long *stats)
+{
+    unsigned long long entries = 0, cells = 0;
+    unsigned int orm[kMaxClasses] = {0, 0, 0, 0};
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < ncell;
+         t += (long long)gridDim.x * blockDim.x) {
+        const unsigned m = mult[t];
+        if (m) {
+            entries += m;
+            cells += 1;
+            const int k = cls[t] & (kMaxClasses - 1);
+#pragma unroll
+            for (int q = 0; q < kMaxClasses; ++q) orm[q] |= (q == k) ? m : 0u;
+        }
+    }
+    for (int off = 16; off; off >>= 1) {
+        entries += __shfl_xor_sync(0xffffffffu, entries, off);
+        cells += __shfl_xor_sync(0xffffffffu, cells, off);
+#pragma unroll
+        for (int q = 0; q < kMaxClasses; ++q) orm[q] |= __shfl_xor_sync(0xffffffffu, orm[q], off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&stats[0], entries);
+        atomicAdd(&stats[1], cells);
+#pragma unroll
+        for (int q = 0; q < kMaxClasses; ++q)
+            if (orm[q]) atomicOr(&stats[2 + q], (unsigned long long)orm[q]);
+    }
+}
+
+cudaError_t launch_grid_stats(const unsigned char *mult, const unsigned char *cls, long long ncell,
+                              unsigned long long *stats, cudaStream_t s)
+{
+    cudaError_t e = cudaMemsetAsync(stats, 0, (2 + kMaxClasses) * sizeof(unsigned long long), s);
+    if (e != cudaSuccess) return e;
+    const int block = 256;
+    const int grid = (int)std::min<long long>((ncell + block - 1) / block, 148 * 8);
+    grid_stats_kernel<<<max(grid, 1), block, 0, s>>>(mult, cls, ncell, stats);
+    return cudaGetLastError();
+}
+
+// one warp per (row, word): lane b reads cell i = 32w + b + 1 and the ballot is the plane word
+__global__ void pack_planes_kernel(const unsigned char *__restrict__ mult, const unsigned char *__restrict__ cls,
+                                   const __grid_constant__ GridDesc g, uint32_t *__restrict__ planes)
+{
+    const long long warp_global = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long n_words = (long long)g.ny * g.stride;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long t = warp_global; t < n_words; t += n_warps) {
+        const int row = (int)(t / g.stride), w = (int)(t % g.stride);
+        const int i = 32 * w + lane; // 0-based column
+        unsigned m = 0, k = 0;
+        if (w < g.wpr && i < g.nx) {
+            const long long cell = (long long)i + (long long)g.nx * row;
+            m = mult[cell];
+            k = cls[cell];
+        }
+        for (int l = 0; l < g.n_planes; ++l) {
+            const bool bit = (m & (unsigned)g.plane_mult[l]) && ((int)k == g.plane_class[l]);
+            const uint32_t word = __ballot_sync(0xffffffffu, bit);
+            if (lane == 0) planes[(size_t)l * g.plane_words + t] = word;
+        }
+    }
+}
+
+cudaError_t launch_pack_planes(const unsigned char *mult, const unsigned char *cls, const GridDesc &g,
+                               uint32_t *planes, cudaStream_t s)
+{
+    cudaError_t e = cudaMemsetAsync(planes, 0, (size_t)g.n_planes * g.plane_words * 4, s);
+    if (e != cudaSuccess) return e;
+    const long long n_words = (long long)g.ny * g.stride;
+    const int block = 256;
+    const int grid = (int)std::min<long long>((n_words * 32 + block - 1) / block, 148 * 16);
+    pack_planes_kernel<<<max(grid, 1), block, 0, s>>>(mult, cls, g, planes);
+    return cudaGetLastError();
+}
+
+__global__ void fill_full_kernel(unsigned char *mult, unsigned char *cls, long long ncell)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < ncell;
+         t += (long long)gridDim.x * blockDim.x) {
+        mult[t] = 1;
+        cls[t] = 0;
+    }
+}
+cudaError_t launch_fill_full(unsigned char *mult, unsigned char *cls, long long ncell, cudaStream_t s)
+{
+    const int block = 256;
+    const int grid = (int)std::min<long long>((ncell + block - 1) / block, 148 * 8);
+    fill_full_kernel<<<max(grid, 1), block, 0, s>>>(mult, cls, ncell);
+    return cudaGetLastError();
+}
+
+__global__ void bits_to_cells_kernel(const uint32_t *__restrict__ bits, int nx, int ny, unsigned char *mult,
+                                     unsigned char *cls)
+{
+    const int wpr = (nx + 31) / 32;
+    const long long ncell = (long long)nx * ny;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < ncell;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t % nx), j = (int)(t / nx);
+        const uint32_t w = bits[(size_t)j * wpr + (i >> 5)];
+        mult[t] = (w >> (i & 31)) & 1u;
+        cls[t] = 0;
+    }
+}
+cudaError_t launch_bits_to_cells(const uint32_t *bits, int nx, int ny, unsigned char *mult,
+                                 unsigned char *cls, cudaStream_t s)
+{
+    const long long ncell = (long long)nx * ny;
+    const int block = 256;
+    const int grid = (int)std::min<long long>((ncell + block - 1) / block, 148 * 8);
+    bits_to_cells_kernel<<<max(grid, 1), block, 0, s>>>(bits, nx, ny, mult, cls);
+    return cudaGetLastError();
+}
+
+__global__ void thresholds_kernel(const double *xyR, int N, double *xyT)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < N) {
+        xyT[c] = xyR[c];
+        xyT[N + c] = xyR[N + c];
+        xyT[2 * N + c] = threshold(xyR[2 * N + c]);
+    }
+}
+cudaError_t launch_thresholds(const double *xyR, int N, double *xyT, cudaStream_t s)
+{
+    thresholds_kernel<<<(N + 127) / 128, 128, 0, s>>>(xyR, N, xyT);
+    return cudaGetLastError();
+}
+
+// exact FP64 test of one cell against N discs (same predicate as calculateArea)
+__device__ __forceinline__ bool cell_covered(const GridDesc &g, int i1, int j1, const double *xyT, int N)
+{
+    const double px = cell_centre(i1, g.dx, g.hdx);
+    const double py = cell_centre(j1, g.dy, g.hdy);
+    for (int c = 0; c < N; ++c)
+        if (radicand(px, py, xyT[c], xyT[N + c]) < xyT[2 * N + c]) return true;
+    return false;
+}
+
+__global__ void remove_covered_kernel(unsigned char *mult, const __grid_constant__ GridDesc g,
+                                      const double *__restrict__ xyT, int N, unsigned long long *removed)
+{
+    const long long ncell = (long long)g.nx * g.ny;
+    unsigned long long mine = 0;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < ncell;
+         t += (long long)gridDim.x * blockDim.x) {
+        const unsigned m = mult[t];
+        if (m) {
+            const int i1 = (int)(t % g.nx) + 1, j1 = (int)(t / g.nx) + 1;
+            if (cell_covered(g, i1, j1, xyT, N)) {
+                mine += m;
+                mult[t] = 0;
+            }
+        }
+    }
+    for (int off = 16; off; off >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, off);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(removed, mine);
+}
+cudaError_t launch_remove_covered(unsigned char *mult, const GridDesc &g, const double *xyT, int N,
+                                  unsigned long long *removed, cudaStream_t s)
+{
+    cudaError_t e = cudaMemsetAsync(removed, 0, sizeof(unsigned long long), s);
+    if (e != cudaSuccess) return e;
+    const long long ncell = (long long)g.nx * g.ny;
+    const int block = 256;
+    const int grid = (int)std::min<long long>((ncell + block - 1) / block, 148 * 8);
+    remove_covered_kernel<<<max(grid, 1), block, 0, s>>>(mult, g, xyT, N, removed);
+    return cudaGetLastError();
+}
+
+__global__ void covered_mask_kernel(unsigned char *mask, const __grid_constant__ GridDesc g,
+                                    const double *__restrict__ xyT, int N)
+{
+    const long long ncell = (long long)g.nx * g.ny;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < ncell;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int i1 = (int)(t % g.nx) + 1, j1 = (int)(t / g.nx) + 1;
+        mask[t] = cell_covered(g, i1, j1, xyT, N) ? 1 : 0;
+    }
+}
+cudaError_t launch_covered_mask(unsigned char *mask, const GridDesc &g, const double *xyT, int N,
+                                cudaStream_t s)
+{
+    const long long ncell = (long long)g.nx * g.ny;
+    const int block = 256;
+    const int grid = (int)std::min<long long>((ncell + block - 1) / block, 148 * 8);
+    covered_mask_kernel<<<max(grid, 1), block, 0, s>>>(mask, g, xyT, N);
+    return cudaGetLastError();
+}
+
+// append list entries: multiplicities add up (saturation reported through *overflow)
+__global__ void add_points_kernel(unsigned char *mult, unsigned char *cls, const int *__restrict__ cell_idx,
+                                  const unsigned char *__restrict__ cell_cls, long long P, int *overflow)
+{
+    // several entries may hit one cell: serialise per cell with a word-wide atomic on the byte's word
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < P;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int cell = cell_idx[t];
+        unsigned int *word = reinterpret_cast<unsigned int *>(mult + (cell & ~3));
+        const int sh = (cell & 3) * 8;
+        unsigned int old = *word, assumed;
+        do {
+            assumed = old;
+            const unsigned m = (assumed >> sh) & 0xffu;
+            if (m >= 255u) {
+                atomicExch(overflow, 1);
+                break;
+            }
+            if (m != 0 && cls[cell] != cell_cls[t]) atomicExch(overflow, 2); // mixed weights on one cell
+            old = atomicCAS(word, assumed, assumed + (1u << sh));
+        } while (old != assumed);
+        cls[cell] = cell_cls[t];
+    }
+}
+cudaError_t launch_add_points(unsigned char *mult, unsigned char *cls, const int *cell_idx,
+                              const unsigned char *cell_cls, long long P, int *overflow, cudaStream_t s)
+{
+    if (P <= 0) return cudaSuccess;
+    const int block = 256;
+    const int grid = (int)std::min<long long>((P + block - 1) / block, 148 * 8);
+    add_points_kernel<<<grid, block, 0, s>>>(mult, cls, cell_idx, cell_cls, P, overflow);
+    return cudaGetLastError();
+}
+
+// ---- poll winner: (min objective, smallest index among ties); NaN objectives never win -----
+__device__ __forceinline__ bool better(double a, long long ia, double b, long long ib)
+{
+    return (a < b) || (a == b && ia < ib);
+}
+__global__ void argmin_stage1(const double *__restrict__ obj, const unsigned char *__restrict__ feasible,
+                              long long B, int barrier, double *so, long long *si)
+{
+    double best = __longlong_as_double(0x7ff0000000000000ll);
+    long long bi = -1;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < B;
+         t += (long long)gridDim.x * blockDim.x) {
+        double v = obj[t];
+        if (barrier && feasible && !feasible[t]) continue;
+        if (v != v) continue;
+        if (bi < 0 || better(v, t, best, bi)) {
+            best = v;
+            bi = t;
+        }
+    }
+    __shared__ double sb[32];
+    __shared__ long long sbi[32];
+    for (int off = 16; off; off >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+        const long long oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        if (oi >= 0 && (bi < 0 || better(ob, oi, best, bi))) {
+            best = ob;
+            bi = oi;
+        }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        sb[warp] = best;
+        sbi[warp] = bi;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = blockDim.x >> 5;
+        best = lane < nw ? sb[lane] : __longlong_as_double(0x7ff0000000000000ll);
+        bi = lane < nw ? sbi[lane] : -1;
+        for (int off = 16; off; off >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+            const long long oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (oi >= 0 && (bi < 0 || better(ob, oi, best, bi))) {
+                best = ob;
+                bi = oi;
+            }
+        }
+        if (lane == 0) {
+            so[blockIdx.x] = best;
+            si[blockIdx.x] = bi;
+        }
+    }
+}
+__global__ void argmin_stage2(double *so, long long *si, int n)
+{
+    // one warp folds the per-block partials into slot 0
+    const int lane = threadIdx.x;
+    double best = __longlong_as_double(0x7ff0000000000000ll);
+    long long bi = -1;
+    for (int t = lane; t < n; t += 32) {
+        const double v = so[t];
+        const long long i = si[t];
+        if (i >= 0 && (bi < 0 || better(v, i, best, bi))) {
+            best = v;
+            bi = i;
+        }
+    }
+    for (int off = 16; off; off >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+        const long long oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        if (oi >= 0 && (bi < 0 || better(ob, oi, best, bi))) {
+            best = ob;
+            bi = oi;
+        }
+    }
+    if (lane == 0) {
+        so[0] = best;
+        si[0] = bi;
+    }
+}
+cudaError_t launch_argmin(const double *obj, const unsigned char *feasible, long long B, int barrier,
+                          double *scratch_obj, long long *scratch_idx, int scratch_n, cudaStream_t s)
+{
+    const int block = 256;
+    int grid = (int)std::min<long long>((B + block - 1) / block, (long long)scratch_n);
+    grid = max(grid, 1);
+    argmin_stage1<<<grid, block, 0, s>>>(obj, feasible, B, barrier, scratch_obj, scratch_idx);
+    argmin_stage2<<<1, 32, 0, s>>>(scratch_obj, scratch_idx, grid);
+    return cudaGetLastError();
+}
+
+// ---- synthetic candidates on the device: Philox4x32-10, counter = (index lo, index hi, uav, draw),
+//      key = (seed lo, seed hi). The host reproduces the same stream (synth.py). ----
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4])
+{
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0;
+        c1 = n1;
+        c2 = n2;
+        c3 = n3;
+        k0 += W0;
+        k1 += W1;
+    }
+    out[0] = c0;
+    out[1] = c1;
+    out[2] = c2;
+    out[3] = c3;
+}
+__device__ __forceinline__ double u01_53(uint32_t a, uint32_t b)
+{
+    // 53 random bits -> [0, 1)
+    const unsigned long long v = ((unsigned long long)(a >> 5) << 26) | (unsigned long long)(b >> 6);
+    return __dmul_rn((double)v, 1.1102230246251565e-16); // 2^-53
+}
+__global__ void generate_kernel(double *X, long long B, int N, unsigned long long seed, long long first, double lx,
+                                double ly, double h_min, double h_max, double tan_half_fov)
+{
+    const long long total = B * N;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long b = t / N;
+        const int u = (int)(t % N);
+        const unsigned long long idx = (unsigned long long)(first + b);
+        uint32_t r[4], q[4];
+        philox4x32_10((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+        philox4x32_10((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)u, 1u, (uint32_t)seed, (uint32_t)(seed >> 32), q);
+        const double x = __dmul_rn(u01_53(r[0], r[1]), lx);
+        const double y = __dmul_rn(u01_53(r[2], r[3]), ly);
+        const double h = __dadd_rn(h_min, __dmul_rn(u01_53(q[0], q[1]), __dsub_rn(h_max, h_min)));
+        double *row = X + b * 3 * N;
+        row[u] = x;
+        row[N + u] = y;
+        row[2 * N + u] = __dmul_rn(h, tan_half_fov);
+    }
+}
+cudaError_t launch_generate(double *dX, long long B, int N, unsigned long long seed, long long first,
+                            double lx, double ly, double h_min, double h_max, double tan_half_fov,
+                            cudaStream_t s)
+{
+    if (B <= 0) return cudaSuccess;
+    const int block = 256;
+    const int grid = (int)std::min<long long>((B * N + block - 1) / block, 148 * 16);
+    generate_kernel<<<grid, block, 0, s>>>(dX, B, N, seed, first, lx, ly, h_min, h_max, tan_half_fov);
+    return cudaGetLastError();
+}
+
+} // namespace cov

@@ -1,0 +1,912 @@
+// cov_kernels.cu -- the batched coverage-objective kernels of libcoverage_cuda (sm_100a).
+//
+// What is computed, per candidate x = [x_1..x_N, y_1..y_N, R_1..R_N] (all citations relative to
+// /root/reference/):
+//   area   = sum over list entries p of w_p * [exists c: sqrt((px-cx)^2 + (py-cy)^2) < R_c]
+//                                                    src/AreaCoverageCalculation.jl:63-110
+//   obj    = -area + penalty_scale * sum_i |R_i - r_max_i|      src/TDM_STATIC_opt.jl:82-100
+//   cons3  : sqrt(dx^2+dy^2+dz^2) > d_lim[i] rejects, z = R/tan(FOV/2)   src/TDM_Constraints.jl:54-75
+//   cons7  : y < 200 and R > 19*tan(FOV/2) rejects                      src/TDM_Constraints.jl:142-154
+//   cons8  : sqrt((xi-xj)^2+(yi-yj)^2) < sep rejects                    src/TDM_Constraints.jl:157-172
+//   cons1_progressive = sum max(R_i - r_max_i, 0)                       src/TDM_Constraints.jl:182-195
+//
+// The list lives on a lattice, so it is held as bit planes (cov_types.h). Three kernels share one
+// per-candidate prologue (thresholds, penalty, constraints):
+//   span   (default) per (disc, row) the covered columns are ONE interval [lo, hi] (the FP64
+//          radicand is monotone in |px - cx|).  Its two ends are estimated in FP32, certified
+//          with an FP32 error band, and decided in FP64 when the band cannot; the interval is
+//          OR-ed into a per-warp shared-memory framebuffer row and the NEWLY set bits are
+//          AND-ed with the fire words and popcounted, which is exactly the reference's
+//          first-covering-disc-wins union count.
+//   brute  every cell against every disc (north_star's formulation): FP32 test with the same
+//          band, FP64 for band cells, ballot + popc.
+//   exact  every cell against every disc in FP64 only (cross-check for the other two).
+// One warp owns one candidate at a time; a CTA is a batch of warps sharing the staged planes.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdint>
+#include "cov_device.cuh"
+#include "cov_kernels.cuh"
+#include "../../include/coverage_cuda.h"
+
+namespace cov {
+
+// ------------------------------------------------------------------------------------------
+// per-disc parameters, one 32-byte record per disc in the owning warp's shared memory
+// ------------------------------------------------------------------------------------------
+struct __align__(16) DiscParam {
+    double T;        // s < T  <=>  sqrt(s) < R
+    float cxf, cyf;  // FP32 roundings of the centre
+    float tlo, thi;  // FP32 radicand below tlo: certainly inside; above thi: certainly outside
+    float Tf;        // (float)T, for the span-end estimate
+    uint32_t rows;   // r0 | r1 << 16: rows that can hold covered cells (1-based); r0 > r1: none
+};
+static_assert(sizeof(DiscParam) == 32, "DiscParam must be 32 bytes");
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ float int_to_float_small(int i)
+{
+    // exact for 0 <= i < 2^23, one LOP3 + one FADD instead of an I2F conversion
+    return __int_as_float(0x4B000000 | i) - 8388608.0f;
+}
+
+// Julia's max(a, 0.0) for Float64: NaN propagates, max(-0.0, 0.0) = 0.0.
+__device__ __forceinline__ double julia_max0(double v) { return (v != v) ? v : (v > 0.0 ? v : 0.0); }
+
+// Results of the prologue that every lane holds after the call.
+struct CandScalars {
+    double violation;   // sum |R_i - r_max_i| in index order
+    double progressive; // sum max(R_i - r_max_i, 0)
+    int feasible;
+};
+
+// Per-candidate prologue, executed by one warp.
+//   stage : the candidate's 3N doubles in shared memory (already visible to the warp)
+//   dp    : N DiscParam records to fill
+template <bool WANT_DP>
+__device__ __forceinline__ CandScalars candidate_prologue(const GridDesc &g, const ObjParams &o,
+                                                          const double *stage, DiscParam *dp,
+                                                          bool want_progressive)
+{
+    const int N = o.N;
+    const uint32_t lane = lane_id();
+    if (WANT_DP) {
+        for (int c = lane; c < N; c += 32) {
+            const double cx = stage[c], cy = stage[N + c], R = stage[2 * N + c];
+            const double T = threshold(R);
+            DiscParam d;
+            d.T = T;
+            d.cxf = (float)cx;
+            d.cyf = (float)cy;
+            d.Tf = (float)T;
+            bool live = (T > 0.0) && (fabs(cx) <= 1.7976931348623157e308) &&
+                        (fabs(cy) <= 1.7976931348623157e308);
+            int r0 = 1, r1 = 0;
+            if (live) {
+                if (isinf(R)) {
+                    r0 = 1;
+                    r1 = g.ny;
+                } else {
+                    // rows j with |py_j - cy| < R, widened by one row and by the FP64 absorption
+                    // error of fl(py - cy) for far-away centres
+                    const double extra = (fabs(cy) + R) * 8.8817841970012523e-16 * g.inv_dy; // 2^-50
+                    double lo = floor((cy - R) * g.inv_dy + 0.5 - extra);
+                    double hi = ceil((cy + R) * g.inv_dy + 0.5 + extra);
+                    if (!(lo <= (double)g.ny) || !(hi >= 1.0)) {
+                        live = false;
+                    } else {
+                        lo = fmax(lo, 1.0);
+                        hi = fmin(hi, (double)g.ny);
+                        r0 = (int)lo;
+                        r1 = (int)hi;
+                    }
+                }
+            }
+            if (!live) {
+                r0 = 1;
+                r1 = 0;
+            }
+            d.rows = (uint32_t)r0 | ((uint32_t)r1 << 16);
+            // FP32 error band on the radicand (derivation in DESIGN.md):
+            //   |s_f32 - s_real| <= 4*sqrt(s)*E + 2*E^2 + 2^-21*s,  E = 2^-21 * max(|cx|,|cy|,extent)
+            // doubled for slack. Outside the window where that algebra holds, certify nothing.
+            const float M = fmaxf(fmaxf(fabsf(d.cxf), fabsf(d.cyf)), g.extent);
+            const float E = M * 4.76837158203125e-07f; // 2^-21
+            const float Tf = d.Tf;
+            if (Tf < 1e30f && M < 1e12f) {
+                const float delta = 2.0f * (4.0f * sqrtf(Tf) * E + 2.0f * E * E + Tf * 9.5367431640625e-07f);
+                d.thi = Tf + delta;
+                d.tlo = (Tf > 64.0f * E * E) ? (Tf - delta) : -1.0f;
+            } else {
+                d.thi = __int_as_float(0x7f800000); // +Inf: nothing is certainly outside
+                d.tlo = -1.0f;                      // nothing is certainly inside
+            }
+            dp[c] = d;
+        }
+    }
+    CandScalars r;
+    // --- penalty: strictly sequential FP64 sum in index order (one lane), then broadcast ---
+    double viol = 0.0, prog = 0.0;
+    if (lane == 0) {
+        for (int i = 0; i < N; ++i) {
+            const double diff = __dsub_rn(stage[2 * N + i], o.r_max[i]);
+            viol = __dadd_rn(viol, fabs(diff));
+        }
+        if (want_progressive)
+            for (int i = 0; i < N; ++i) {
+                const double diff = __dsub_rn(stage[2 * N + i], o.r_max[i]);
+                prog = __dadd_rn(prog, julia_max0(diff));
+            }
+    }
+    r.violation = __shfl_sync(0xffffffffu, viol, 0);
+    r.progressive = __shfl_sync(0xffffffffu, prog, 0);
+    // --- extreme constraints: order-free (a conjunction), so lane-parallel ---
+    bool bad = false;
+    if (o.use_cons3) {
+        for (int i = lane; i < N; i += 32) {
+            const double ax = __dsub_rn(o.prev_x[i], stage[i]);
+            const double ay = __dsub_rn(o.prev_y[i], stage[N + i]);
+            const double z2 = __ddiv_rn(stage[2 * N + i], o.tan_half_fov);
+            const double az = __dsub_rn(o.prev_z[i], z2);
+            const double s =
+                __dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az));
+            bad |= (s >= o.cons3_G[i]);
+        }
+    }
+    if (o.use_cons7) {
+        for (int i = lane; i < N; i += 32)
+            bad |= (stage[N + i] < 200.0) && (stage[2 * N + i] > o.cons7_R);
+    }
+    if (o.use_cons8) {
+        // (xi-xj)^2 is symmetric in i, j, so unordered pairs decide the ordered-pair loop
+        for (int i = 0; i < N - 1; ++i) {
+            const double xi = stage[i], yi = stage[N + i];
+            for (int j = i + 1 + lane; j < N; j += 32) {
+                const double ax = __dsub_rn(xi, stage[j]);
+                const double ay = __dsub_rn(yi, stage[N + j]);
+                const double s = __dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay));
+                bad |= (s < o.sep_T);
+            }
+            if (__any_sync(0xffffffffu, bad)) break;
+        }
+    }
+    r.feasible = !__any_sync(0xffffffffu, bad);
+    return r;
+}
+
+// obj = -area + violation*scale, area from exact integer counts (see cov_grid_info.area_exact)
+__device__ __forceinline__ double assemble_objective(const GridDesc &g, const ObjParams &o,
+                                                     const long long *class_cnt, double violation)
+{
+    double area = 0.0;
+    if (g.n_classes == 1) {
+        area = __dmul_rn(g.class_weight[0], (double)class_cnt[0]);
+    } else {
+        for (int k = 0; k < g.n_classes; ++k)
+            area = __dadd_rn(area, __dmul_rn(g.class_weight[k], (double)class_cnt[k]));
+    }
+    return __dadd_rn(-area, __dmul_rn(violation, o.penalty_scale));
+}
+
+// ------------------------------------------------------------------------------------------
+// exact FP64 pieces of the span search
+// ------------------------------------------------------------------------------------------
+struct RowExact {
+    double cx, T, dy2, dx, hdx;
+    int nx;
+    __device__ __forceinline__ double px(int i) const { return cell_centre(i, dx, hdx); }
+    __device__ __forceinline__ bool inside(int i) const
+    {
+        const double ddx = __dsub_rn(px(i), cx);
+        return __dadd_rn(__dmul_rn(ddx, ddx), dy2) < T;
+    }
+};
+
+// Exact [lo, hi] (1-based, inclusive; lo > hi: empty) of the covered columns of one row, walking
+// from the estimates. Correct for ANY estimates: the covered set is contiguous and, if not empty,
+// contains a cell next to the centre, because the FP64 radicand is non-increasing in i while
+// px_i <= cx and non-decreasing while px_i >= cx (every rounding involved is monotone).
+__device__ __noinline__ void exact_span(const RowExact r, int lo_e, int hi_e, int &lo_out, int &hi_out)
+{
+    int i = min(max(lo_e, 1), r.nx);
+    bool found = false;
+    if (r.inside(i)) {
+        found = true;
+    } else if (r.px(i) < r.cx) { // left of the centre: the span, if any, starts to the right
+        for (;;) {
+            ++i;
+            if (i > r.nx) break;
+            if (r.inside(i)) {
+                found = true;
+                break;
+            }
+            if (!(r.px(i) < r.cx)) break; // passed the centre without a hit: empty row
+        }
+    } else { // at or right of the centre
+        for (;;) {
+            --i;
+            if (i < 1) break;
+            if (r.inside(i)) {
+                found = true;
+                break;
+            }
+            if (!(r.px(i) > r.cx)) break;
+        }
+    }
+    if (!found) {
+        lo_out = 1;
+        hi_out = 0;
+        return;
+    }
+    int lo = i;
+    while (lo > 1 && r.inside(lo - 1)) --lo;
+    int h = min(max(hi_e, i), r.nx);
+    if (r.inside(h)) {
+        while (h < r.nx && r.inside(h + 1)) ++h;
+    } else {
+        while (!r.inside(h)) --h; // stops at i at the latest
+    }
+    lo_out = lo;
+    hi_out = h;
+}
+
+// ------------------------------------------------------------------------------------------
+// shared-memory plumbing
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// TMA bulk copy global -> shared (1-D, 16-byte granular), completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+template <bool SMEM>
+__device__ __forceinline__ uint32_t ld_plane(const uint32_t *p)
+{
+    return SMEM ? *p : __ldg(p);
+}
+
+struct WarpSmem {
+    uint32_t *fb;   // framebuffer band
+    double *stage;  // 3N doubles
+    DiscParam *dp;  // N records
+};
+
+__host__ __device__ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+struct SmemPlan {
+    int planes_bytes;  // 0 when the planes stay in global memory
+    int fb_words;      // per warp
+    int warp_bytes;    // per warp, multiple of 16
+    int total_bytes;
+};
+__host__ __device__ inline SmemPlan plan_smem(const GridDesc &g, int N, int warps, int band_rows,
+                                              bool planes_in_smem, bool want_fb)
+{
+    SmemPlan p;
+    p.planes_bytes = planes_in_smem ? g.n_planes * g.plane_words * 4 : 0;
+    p.fb_words = want_fb ? round_up(band_rows * g.stride, 4) : 0;
+    p.warp_bytes = p.fb_words * 4 + round_up(3 * N * 8, 16) + N * 32;
+    p.total_bytes = p.planes_bytes + warps * p.warp_bytes + 16;
+    return p;
+}
+
+__device__ __forceinline__ void stage_planes(const GridDesc &g, uint32_t *planes_s, uint64_t *bar,
+                                             int planes_bytes)
+{
+    // one elected thread issues TMA bulk copies of the (pre-padded) planes; everyone waits
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, (uint32_t)planes_bytes);
+        const char *src = reinterpret_cast<const char *>(g.planes);
+        char *dst = reinterpret_cast<char *>(planes_s);
+        int left = planes_bytes;
+        while (left > 0) {
+            const int n = left > 65536 ? 65536 : left;
+            bulk_g2s(dst, src, (uint32_t)n, bar);
+            dst += n;
+            src += n;
+            left -= n;
+        }
+    }
+    mbar_wait(bar, 0);
+}
+
+// ------------------------------------------------------------------------------------------
+// span kernel
+// ------------------------------------------------------------------------------------------
+// MULTI = false: one plane, one class, multiplicity 1 (the static grid and synthetic fire grids).
+template <bool MULTI, bool PLANES_SMEM>
+__global__ void __launch_bounds__(512)
+span_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjParams o,
+            const double *__restrict__ X, long long B, EvalOut out, unsigned long long *counter,
+            int band_rows, int force_exact)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t lane = lane_id();
+    const int N = o.N;
+    const SmemPlan plan = plan_smem(g, N, warps, band_rows, PLANES_SMEM, true);
+    uint32_t *planes_s = reinterpret_cast<uint32_t *>(smem_raw);
+    unsigned char *wbase = smem_raw + plan.planes_bytes + (size_t)warp * plan.warp_bytes;
+    uint32_t *fb = reinterpret_cast<uint32_t *>(wbase);
+    double *stage = reinterpret_cast<double *>(wbase + plan.fb_words * 4);
+    DiscParam *dp = reinterpret_cast<DiscParam *>(wbase + plan.fb_words * 4 + round_up(3 * N * 8, 16));
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + plan.planes_bytes + (size_t)warps * plan.warp_bytes);
+
+    if (PLANES_SMEM) stage_planes(g, planes_s, bar, plan.planes_bytes);
+    const uint32_t *planes = PLANES_SMEM ? planes_s : g.planes;
+
+    // clear this warp's framebuffer once; it is cleared again after every band that touched it
+    for (int t = lane; t < plan.fb_words / 4; t += 32) reinterpret_cast<uint4 *>(fb)[t] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+
+    const int n_bands = (g.ny + band_rows - 1) / band_rows;
+    const long long n_chunks = (B + 31) / 32;
+    const int cstride = 3 * N;
+
+    for (;;) {
+        unsigned long long chunk = 0;
+        if (lane == 0) chunk = atomicAdd(counter, 1ull);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if ((long long)chunk >= n_chunks) break;
+        const long long base = (long long)chunk * 32;
+        const int in_chunk = (int)min(32ll, B - base);
+
+        double my_obj = 0.0, my_prog = 0.0;
+        long long my_cnt = 0;
+        long long my_cls[kMaxClasses];
+#pragma unroll
+        for (int k = 0; k < kMaxClasses; ++k) my_cls[k] = 0;
+        int my_feas = 0;
+
+        for (int kc = 0; kc < in_chunk; ++kc) {
+            const double *xc = X + (base + kc) * cstride;
+            for (int t = lane; t < cstride; t += 32) stage[t] = __ldg(xc + t);
+            __syncwarp();
+            const CandScalars cs = candidate_prologue<true>(g, o, stage, dp, out.progressive != nullptr);
+            __syncwarp();
+
+            uint32_t cnt[MULTI ? kMaxClasses : 1];
+#pragma unroll
+            for (int k = 0; k < (MULTI ? kMaxClasses : 1); ++k) cnt[k] = 0;
+
+            for (int band = 0; band < n_bands; ++band) {
+                const int band_lo = band * band_rows + 1;
+                const int band_hi = min(g.ny, band_lo + band_rows - 1);
+                bool touched = false;
+                for (int cb = 0; cb < N; cb += 32) {
+                    const int cme = cb + lane;
+                    bool hit = false;
+                    if (cme < N) {
+                        const uint32_t rows = dp[cme].rows;
+                        const int r0 = rows & 0xffff, r1 = rows >> 16;
+                        hit = (r0 <= r1) && (r0 <= band_hi) && (r1 >= band_lo);
+                    }
+                    uint32_t hits = __ballot_sync(0xffffffffu, hit);
+                    while (hits) {
+                        const int c = cb + __ffs(hits) - 1;
+                        hits &= hits - 1;
+                        touched = true;
+                        const DiscParam d = dp[c];
+                        const int rs = max((int)(d.rows & 0xffff), band_lo);
+                        const int re = min((int)(d.rows >> 16), band_hi);
+                        for (int row0 = rs; row0 <= re; row0 += 32) {
+                            const int j = row0 + lane;
+                            if (j <= re) {
+                                // ---- FP32 estimate of the span ends ----
+                                const float pyf = fmaf(int_to_float_small(j), g.dyf, -g.hdyf);
+                                const float ddy = pyf - d.cyf;
+                                const float dy2 = ddy * ddy;
+                                bool empty = !force_exact && (dy2 > d.thi);
+                                int lo = 1, hi = 0;
+                                if (!empty) {
+                                    const float w = sqrtf(fmaxf(d.Tf - dy2, 0.0f));
+                                    int lo_e = __float2int_rd(fmaf(d.cxf - w, g.inv_dxf, 0.5f)) + 1;
+                                    int hi_e = __float2int_ru(fmaf(d.cxf + w, g.inv_dxf, 0.5f)) - 1;
+                                    lo_e = max(lo_e, 1);
+                                    hi_e = min(hi_e, g.nx);
+                                    bool slow = force_exact || (lo_e > hi_e);
+                                    if (!slow) {
+                                        // certify: lo_e inside, lo_e-1 outside, hi_e inside, hi_e+1 outside
+                                        const float x_lo = fmaf(int_to_float_small(lo_e), g.dxf, -g.hdxf) - d.cxf;
+                                        const float x_hi = fmaf(int_to_float_small(hi_e), g.dxf, -g.hdxf) - d.cxf;
+                                        const float s_lo = fmaf(x_lo, x_lo, dy2);
+                                        const float s_hi = fmaf(x_hi, x_hi, dy2);
+                                        const float x_lm = x_lo - g.dxf, x_hp = x_hi + g.dxf;
+                                        const float s_lm = fmaf(x_lm, x_lm, dy2);
+                                        const float s_hp = fmaf(x_hp, x_hp, dy2);
+                                        const bool ok = (s_lo < d.tlo) && (s_hi < d.tlo) &&
+                                                        (lo_e == 1 || s_lm > d.thi) &&
+                                                        (hi_e == g.nx || s_hp > d.thi);
+                                        slow = !ok;
+                                        lo = lo_e;
+                                        hi = hi_e;
+                                    }
+                                    if (slow) {
+                                        RowExact r;
+                                        r.cx = stage[c];
+                                        r.T = d.T;
+                                        r.dx = g.dx;
+                                        r.hdx = g.hdx;
+                                        r.nx = g.nx;
+                                        const double ddyd = __dsub_rn(cell_centre(j, g.dy, g.hdy), stage[N + c]);
+                                        r.dy2 = __dmul_rn(ddyd, ddyd);
+                                        exact_span(r, lo_e, hi_e, lo, hi);
+                                    }
+                                }
+                                if (lo <= hi) {
+                                    const int a = lo - 1, b = hi - 1;
+                                    const int wa = a >> 5, wb = b >> 5;
+                                    uint32_t *frow = fb + (j - band_lo) * g.stride;
+                                    const uint32_t *prow = planes + (size_t)(j - 1) * g.stride;
+                                    for (int w = wa; w <= wb; ++w) {
+                                        uint32_t m = 0xffffffffu;
+                                        if (w == wa) m &= 0xffffffffu << (a & 31);
+                                        if (w == wb) m &= 0xffffffffu >> (31 - (b & 31));
+                                        const uint32_t old = frow[w];
+                                        const uint32_t nw = m & ~old;
+                                        if (nw) {
+                                            frow[w] = old | m;
+                                            if (!MULTI) {
+                                                cnt[0] += __popc(nw & ld_plane<PLANES_SMEM>(prow + w));
+                                            } else {
+                                                for (int l = 0; l < g.n_planes; ++l) {
+                                                    const uint32_t v =
+                                                        __popc(nw & ld_plane<PLANES_SMEM>(
+                                                                        prow + (size_t)l * g.plane_words + w)) *
+                                                        g.plane_mult[l];
+                                                    const int kcls = g.plane_class[l];
+#pragma unroll
+                                                    for (int k = 0; k < kMaxClasses; ++k)
+                                                        cnt[k] += (k == kcls) ? v : 0u;
+                                                }
+                                            }
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                        __syncwarp(); // rows of the next disc may be other lanes' rows of this one
+                    }
+                }
+                if (touched) {
+                    const int words = (band_hi - band_lo + 1) * g.stride;
+                    for (int t = lane; t < (words + 3) / 4; t += 32)
+                        reinterpret_cast<uint4 *>(fb)[t] = make_uint4(0, 0, 0, 0);
+                    __syncwarp();
+                }
+            }
+
+            long long cls_total[kMaxClasses];
+            long long total = 0;
+#pragma unroll
+            for (int k = 0; k < kMaxClasses; ++k) {
+                cls_total[k] = 0;
+                if (k < (MULTI ? kMaxClasses : 1)) {
+                    cls_total[k] = (long long)__reduce_add_sync(0xffffffffu, cnt[k]);
+                    total += cls_total[k];
+                }
+            }
+            const double objv = assemble_objective(g, o, cls_total, cs.violation);
+            if ((int)lane == kc) {
+                my_obj = objv;
+                my_cnt = total;
+                my_feas = cs.feasible;
+                my_prog = cs.progressive;
+#pragma unroll
+                for (int k = 0; k < kMaxClasses; ++k) my_cls[k] = cls_total[k];
+            }
+            __syncwarp(); // stage/dp are rewritten by the next candidate
+        }
+        // coalesced write of the chunk's 32 results
+        if ((int)lane < in_chunk) {
+            const long long bidx = base + lane;
+            out.obj[bidx] = my_obj;
+            if (out.count) out.count[bidx] = my_cnt;
+            if (out.feasible) out.feasible[bidx] = (unsigned char)my_feas;
+            if (out.progressive) out.progressive[bidx] = my_prog;
+            if (out.class_count)
+                for (int k = 0; k < g.n_classes; ++k) out.class_count[bidx * g.n_classes + k] = my_cls[k];
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// brute kernel (north_star's formulation): every cell of every word that holds a list entry is
+// tested against every disc.  Lane b of a warp owns cell 32w + b + 1 of the word being swept; the
+// discs come from the warp's shared memory as one broadcast 16-byte load each
+// (cx, tlo, thi, dy^2 for the current row); FP32 test with the certified band, FP64 for band
+// cells only; ballot + popc against the plane words.
+// ------------------------------------------------------------------------------------------
+template <bool MULTI, bool PLANES_SMEM>
+__global__ void __launch_bounds__(256)
+brute_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjParams o,
+             const double *__restrict__ X, long long B, EvalOut out, unsigned long long *counter,
+             int force_exact)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t lane = lane_id();
+    const int N = o.N;
+    const int planes_bytes = PLANES_SMEM ? g.n_planes * g.plane_words * 4 : 0;
+    const int warp_bytes = round_up(3 * N * 8, 16) + N * 32 + N * 16;
+    uint32_t *planes_s = reinterpret_cast<uint32_t *>(smem_raw);
+    unsigned char *wbase = smem_raw + planes_bytes + (size_t)warp * warp_bytes;
+    double *stage = reinterpret_cast<double *>(wbase);
+    DiscParam *dp = reinterpret_cast<DiscParam *>(wbase + round_up(3 * N * 8, 16));
+    float4 *row = reinterpret_cast<float4 *>(wbase + round_up(3 * N * 8, 16) + N * 32);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + planes_bytes + (size_t)warps * warp_bytes);
+
+    if (PLANES_SMEM) stage_planes(g, planes_s, bar, planes_bytes);
+    const uint32_t *planes = PLANES_SMEM ? planes_s : g.planes;
+
+    const long long n_chunks = (B + 31) / 32;
+    const int cstride = 3 * N;
+    for (;;) {
+        unsigned long long chunk = 0;
+        if (lane == 0) chunk = atomicAdd(counter, 1ull);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if ((long long)chunk >= n_chunks) break;
+        const long long base = (long long)chunk * 32;
+        const int in_chunk = (int)min(32ll, B - base);
+        double my_obj = 0.0, my_prog = 0.0;
+        long long my_cnt = 0;
+        long long my_cls[kMaxClasses];
+#pragma unroll
+        for (int k = 0; k < kMaxClasses; ++k) my_cls[k] = 0;
+        int my_feas = 0;
+
+        for (int kc = 0; kc < in_chunk; ++kc) {
+            const double *xc = X + (base + kc) * cstride;
+            for (int t = lane; t < cstride; t += 32) stage[t] = __ldg(xc + t);
+            __syncwarp();
+            const CandScalars cs = candidate_prologue<true>(g, o, stage, dp, out.progressive != nullptr);
+            __syncwarp();
+            for (int c = lane; c < N; c += 32) {
+                const DiscParam d = dp[c];
+                row[c] = make_float4(d.cxf, force_exact ? -1.0f : d.tlo,
+                                     force_exact ? __int_as_float(0x7f800000) : d.thi, 0.0f);
+            }
+            long long cls_total[kMaxClasses];
+#pragma unroll
+            for (int k = 0; k < kMaxClasses; ++k) cls_total[k] = 0;
+            uint32_t cnt[MULTI ? kMaxClasses : 1];
+#pragma unroll
+            for (int k = 0; k < (MULTI ? kMaxClasses : 1); ++k) cnt[k] = 0;
+
+            for (int j = 1; j <= g.ny; ++j) {
+                const float pyf = fmaf(int_to_float_small(j), g.dyf, -g.hdyf);
+                __syncwarp();
+                for (int c = lane; c < N; c += 32) {
+                    const float ddy = pyf - dp[c].cyf;
+                    row[c].w = ddy * ddy;
+                }
+                __syncwarp();
+                const uint32_t *prow = planes + (size_t)(j - 1) * g.stride;
+                for (int w = 0; w < g.wpr; ++w) {
+                    uint32_t fire = ld_plane<PLANES_SMEM>(prow + w);
+                    if (MULTI)
+                        for (int l = 1; l < g.n_planes; ++l)
+                            fire |= ld_plane<PLANES_SMEM>(prow + (size_t)l * g.plane_words + w);
+                    if (fire == 0) continue; // no list entry on these 32 cells
+                    const int i = 32 * w + (int)lane + 1;
+                    const float pxf = fmaf(int_to_float_small(i), g.dxf, -g.hdxf);
+                    bool covered = false, band = false;
+#pragma unroll 4
+                    for (int c = 0; c < N; ++c) {
+                        const float4 r = row[c];
+                        const float x = pxf - r.x;
+                        const float sf = fmaf(x, x, r.w);
+                        const bool in = sf < r.y;
+                        covered |= in;
+                        band |= !(in || sf > r.z);
+                    }
+                    const bool need = band && !covered && i <= g.nx;
+                    if (__any_sync(0xffffffffu, need)) {
+                        if (need) {
+                            const double px = cell_centre(i, g.dx, g.hdx);
+                            const double py = cell_centre(j, g.dy, g.hdy);
+                            for (int c = 0; c < N; ++c)
+                                if (radicand(px, py, stage[c], stage[N + c]) < dp[c].T) {
+                                    covered = true;
+                                    break;
+                                }
+                        }
+                    }
+                    const uint32_t m = __ballot_sync(0xffffffffu, covered && i <= g.nx);
+                    if (!MULTI) {
+                        cnt[0] += __popc(m & fire);
+                    } else {
+                        for (int l = 0; l < g.n_planes; ++l) {
+                            const uint32_t v =
+                                __popc(m & ld_plane<PLANES_SMEM>(prow + (size_t)l * g.plane_words + w)) *
+                                g.plane_mult[l];
+                            const int kcls = g.plane_class[l];
+#pragma unroll
+                            for (int k = 0; k < kMaxClasses; ++k) cnt[k] += (k == kcls) ? v : 0u;
+                        }
+                    }
+                }
+                if ((j & 1023) == 0) { // keep the 32-bit partial counts far from overflow
+#pragma unroll
+                    for (int k = 0; k < (MULTI ? kMaxClasses : 1); ++k) {
+                        cls_total[k] += cnt[k];
+                        cnt[k] = 0;
+                    }
+                }
+            }
+            long long total = 0;
+#pragma unroll
+            for (int k = 0; k < kMaxClasses; ++k) {
+                if (k < (MULTI ? kMaxClasses : 1)) cls_total[k] += cnt[k]; // ballot counts are warp-uniform
+                total += cls_total[k];
+            }
+            const double objv = assemble_objective(g, o, cls_total, cs.violation);
+            if ((int)lane == kc) {
+                my_obj = objv;
+                my_cnt = total;
+                my_feas = cs.feasible;
+                my_prog = cs.progressive;
+#pragma unroll
+                for (int k = 0; k < kMaxClasses; ++k) my_cls[k] = cls_total[k];
+            }
+            __syncwarp();
+        }
+        if ((int)lane < in_chunk) {
+            const long long bidx = base + lane;
+            out.obj[bidx] = my_obj;
+            if (out.count) out.count[bidx] = my_cnt;
+            if (out.feasible) out.feasible[bidx] = (unsigned char)my_feas;
+            if (out.progressive) out.progressive[bidx] = my_prog;
+            if (out.class_count)
+                for (int k = 0; k < g.n_classes; ++k) out.class_count[bidx * g.n_classes + k] = my_cls[k];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// exact kernel: every cell against every disc, FP64 only. Slow by design; the cross-check.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+exact_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjParams o,
+             const double *__restrict__ X, long long B, EvalOut out, unsigned long long *counter)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5;
+    const uint32_t lane = lane_id();
+    const int N = o.N;
+    const int warp_bytes = round_up(3 * N * 8, 16) + round_up(N * 8, 16);
+    double *stage = reinterpret_cast<double *>(smem_raw + (size_t)warp * warp_bytes);
+    double *Ts = reinterpret_cast<double *>(smem_raw + (size_t)warp * warp_bytes + round_up(3 * N * 8, 16));
+    const int cstride = 3 * N;
+    for (;;) {
+        unsigned long long cand = 0;
+        if (lane == 0) cand = atomicAdd(counter, 1ull);
+        cand = __shfl_sync(0xffffffffu, cand, 0);
+        if ((long long)cand >= B) break;
+        const double *xc = X + (long long)cand * cstride;
+        for (int t = lane; t < cstride; t += 32) stage[t] = xc[t];
+        __syncwarp();
+        for (int c = lane; c < N; c += 32) Ts[c] = threshold(stage[2 * N + c]);
+        const CandScalars cs = candidate_prologue<false>(g, o, stage, nullptr, out.progressive != nullptr);
+        __syncwarp();
+        long long cls_total[kMaxClasses];
+#pragma unroll
+        for (int k = 0; k < kMaxClasses; ++k) cls_total[k] = 0;
+        for (int j = 1; j <= g.ny; ++j) {
+            const double py = cell_centre(j, g.dy, g.hdy);
+            for (int w = 0; w < g.wpr; ++w) {
+                uint32_t any_bits = 0;
+                for (int l = 0; l < g.n_planes; ++l)
+                    any_bits |= g.planes[(size_t)l * g.plane_words + (size_t)(j - 1) * g.stride + w];
+                if (!any_bits) continue;
+                const int i = 32 * w + lane + 1;
+                bool cov_cell = false;
+                if (i <= g.nx) {
+                    const double px = cell_centre(i, g.dx, g.hdx);
+                    for (int c = 0; c < N; ++c) {
+                        if (radicand(px, py, stage[c], stage[N + c]) < Ts[c]) {
+                            cov_cell = true;
+                            break;
+                        }
+                    }
+                }
+                const uint32_t m = __ballot_sync(0xffffffffu, cov_cell);
+                for (int l = 0; l < g.n_planes; ++l) {
+                    const uint32_t pw = g.planes[(size_t)l * g.plane_words + (size_t)(j - 1) * g.stride + w];
+                    cls_total[g.plane_class[l] & (kMaxClasses - 1)] += (long long)__popc(m & pw) * g.plane_mult[l];
+                }
+            }
+        }
+        if (lane == 0) {
+            long long total = 0;
+            for (int k = 0; k < g.n_classes; ++k) total += cls_total[k];
+            out.obj[cand] = assemble_objective(g, o, cls_total, cs.violation);
+            if (out.count) out.count[cand] = total;
+            if (out.feasible) out.feasible[cand] = (unsigned char)cs.feasible;
+            if (out.progressive) out.progressive[cand] = cs.progressive;
+            if (out.class_count)
+                for (int k = 0; k < g.n_classes; ++k) out.class_count[cand * g.n_classes + k] = cls_total[k];
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// launcher
+// ------------------------------------------------------------------------------------------
+static int pick_band_rows(const GridDesc &g, int N, const LaunchCfg &cfg, int warps, bool planes_smem,
+                          int budget)
+{
+    if (cfg.band_rows > 0) return min(cfg.band_rows, g.ny);
+    // whole grid per warp if it fits, else the largest multiple of 32 rows that does
+    int rows = g.ny;
+    for (;;) {
+        SmemPlan p = plan_smem(g, N, warps, rows, planes_smem, true);
+        if (p.total_bytes <= budget) return rows;
+        if (rows <= 32) return 0;
+        rows = (rows > 64) ? round_up(rows / 2, 32) : 32;
+    }
+}
+
+int span_planes_fit_smem(const GridDesc &g, int N, const LaunchCfg &cfg)
+{
+    const int warps = cfg.warps_per_cta > 0 ? cfg.warps_per_cta : 8;
+    const int planes_bytes = g.n_planes * g.plane_words * 4;
+    // the planes are worth staging only if at least a 32-row band per warp still fits beside them
+    SmemPlan p = plan_smem(g, N, warps, min(32, g.ny), true, true);
+    (void)planes_bytes;
+    return p.total_bytes <= cfg.max_smem_optin;
+}
+
+template <typename K>
+static cudaError_t set_smem(K kernel, int bytes)
+{
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+cudaError_t launch_eval(const GridDesc &g, const ObjParams &o, const LaunchCfg &cfg, const double *dX,
+                        long long B, const EvalOut &out, unsigned long long *counter,
+                        cudaStream_t stream, LaunchInfo *info)
+{
+    if (B <= 0) return cudaSuccess;
+    cudaError_t err = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
+    if (err != cudaSuccess) return err;
+    const int N = o.N;
+    LaunchInfo li{};
+    if (cfg.kernel == COV_KERNEL_EXACT) {
+        int warps = 8;
+        while (warps > 1 && warps * (round_up(3 * N * 8, 16) + round_up(N * 8, 16)) > 96 * 1024) warps /= 2;
+        const int smem = warps * (round_up(3 * N * 8, 16) + round_up(N * 8, 16));
+        err = set_smem(exact_kernel, smem);
+        if (err != cudaSuccess) return err;
+        long long want = (B + warps - 1) / warps;
+        const int grid = (int)std::min<long long>(want, (long long)cfg.num_sms * 8);
+        exact_kernel<<<grid, warps * 32, smem, stream>>>(g, o, dX, B, out, counter);
+        li.grid = grid;
+        li.block = warps * 32;
+        li.smem_bytes = smem;
+        if (info) *info = li;
+        return cudaGetLastError();
+    }
+    if (cfg.kernel == COV_KERNEL_BRUTE) {
+        const bool multi = !(g.n_planes == 1 && g.n_classes == 1 && g.plane_mult[0] == 1);
+        int warps = cfg.warps_per_cta > 0 ? min(cfg.warps_per_cta, 8) : 8;
+        const int per_warp = round_up(3 * N * 8, 16) + N * 32 + N * 16;
+        const int planes_bytes = g.n_planes * g.plane_words * 4;
+        while (warps > 1 && warps * per_warp + 16 > cfg.max_smem_optin) warps /= 2;
+        if (warps * per_warp + 16 > cfg.max_smem_optin) return cudaErrorInvalidConfiguration;
+        const bool planes_smem = planes_bytes + warps * per_warp + 16 <= cfg.max_smem_optin;
+        const int smem = (planes_smem ? planes_bytes : 0) + warps * per_warp + 16;
+        const long long chunks = (B + 31) / 32;
+        const long long want = (chunks + warps - 1) / warps;
+        const int per_sm = max(1, min(8, cfg.max_smem_optin / max(smem, 1)));
+        const int grid = (int)std::min<long long>(want, (long long)cfg.num_sms * per_sm);
+        li.grid = grid;
+        li.block = warps * 32;
+        li.smem_bytes = smem;
+        li.planes_in_smem = planes_smem;
+        if (info) *info = li;
+#define COV_LAUNCH_BRUTE(M, S)                                                                      \
+    do {                                                                                            \
+        err = set_smem(brute_kernel<M, S>, smem);                                                   \
+        if (err != cudaSuccess) return err;                                                         \
+        brute_kernel<M, S><<<grid, warps * 32, smem, stream>>>(g, o, dX, B, out, counter,           \
+                                                               cfg.force_exact);                    \
+    } while (0)
+        if (multi) {
+            if (planes_smem) COV_LAUNCH_BRUTE(true, true);
+            else COV_LAUNCH_BRUTE(true, false);
+        } else {
+            if (planes_smem) COV_LAUNCH_BRUTE(false, true);
+            else COV_LAUNCH_BRUTE(false, false);
+        }
+#undef COV_LAUNCH_BRUTE
+        return cudaGetLastError();
+    }
+    // span
+    const bool multi = !(g.n_planes == 1 && g.n_classes == 1 && g.plane_mult[0] == 1);
+    int warps = cfg.warps_per_cta > 0 ? cfg.warps_per_cta : 8;
+    const int ctas_per_sm = cfg.ctas_per_sm > 0 ? cfg.ctas_per_sm : 1;
+    const int budget = cfg.max_smem_optin / ctas_per_sm - (ctas_per_sm > 1 ? 1024 : 0);
+    bool planes_smem = false;
+    {
+        SmemPlan p = plan_smem(g, N, warps, min(32, g.ny), true, true);
+        planes_smem = p.total_bytes <= budget;
+    }
+    int band_rows = pick_band_rows(g, N, cfg, warps, planes_smem, budget);
+    while (band_rows == 0 && warps > 1) { // too many warps for this N / stride: shrink the CTA
+        warps /= 2;
+        band_rows = pick_band_rows(g, N, cfg, warps, planes_smem, budget);
+    }
+    if (band_rows == 0) return cudaErrorInvalidConfiguration;
+    SmemPlan p = plan_smem(g, N, warps, band_rows, planes_smem, true);
+    if (p.total_bytes > cfg.max_smem_optin) return cudaErrorInvalidConfiguration;
+    const long long chunks = (B + 31) / 32;
+    const long long want = (chunks + warps - 1) / warps;
+    const int grid = (int)std::min<long long>(want, (long long)cfg.num_sms * ctas_per_sm);
+    li.grid = grid;
+    li.block = warps * 32;
+    li.smem_bytes = p.total_bytes;
+    li.band_rows = band_rows;
+    li.planes_in_smem = planes_smem;
+    if (info) *info = li;
+#define COV_LAUNCH_SPAN(M, S)                                                                      \
+    do {                                                                                           \
+        err = set_smem(span_kernel<M, S>, p.total_bytes);                                          \
+        if (err != cudaSuccess) return err;                                                        \
+        span_kernel<M, S><<<grid, warps * 32, p.total_bytes, stream>>>(g, o, dX, B, out, counter,  \
+                                                                       band_rows, cfg.force_exact); \
+    } while (0)
+    if (multi) {
+        if (planes_smem) COV_LAUNCH_SPAN(true, true);
+        else COV_LAUNCH_SPAN(true, false);
+    } else {
+        if (planes_smem) COV_LAUNCH_SPAN(false, true);
+        else COV_LAUNCH_SPAN(false, false);
+    }
+#undef COV_LAUNCH_SPAN
+    return cudaGetLastError();
+}
+
+} // namespace cov

@@ -1,0 +1,55 @@
+// cov_kernels.cuh -- launch interface between the C ABI (cov_api.cu) and the kernels
+// (cov_kernels.cu, cov_grid_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "cov_types.h"
+
+namespace cov {
+
+struct LaunchCfg {
+    int kernel;          // COV_KERNEL_*
+    int warps_per_cta;   // 0 = auto
+    int ctas_per_sm;     // 0 = auto
+    int band_rows;       // 0 = auto
+    int force_exact;
+    int num_sms;
+    int max_smem_optin;  // bytes
+};
+
+struct LaunchInfo {
+    int grid, block, smem_bytes, band_rows, planes_in_smem;
+};
+
+// Coverage objective over B candidates (device pointers). counter: one zeroed
+// unsigned long long per launch (work-chunk dispenser). Returns cudaError_t.
+cudaError_t launch_eval(const GridDesc &g, const ObjParams &o, const LaunchCfg &cfg, const double *dX,
+                        long long B, const EvalOut &out, unsigned long long *counter,
+                        cudaStream_t stream, LaunchInfo *info);
+
+// Would the span kernel keep the planes in shared memory for this grid / N?
+int span_planes_fit_smem(const GridDesc &g, int N, const LaunchCfg &cfg);
+
+// ---- cell-store kernels (cov_grid_kernels.cu) ----
+// stats[0] = entries, stats[1] = cells, stats[2 + k] = OR of the multiplicities of class k
+cudaError_t launch_grid_stats(const unsigned char *mult, const unsigned char *cls, long long ncell,
+                              unsigned long long *stats, cudaStream_t s);
+cudaError_t launch_pack_planes(const unsigned char *mult, const unsigned char *cls, const GridDesc &g,
+                               uint32_t *planes, cudaStream_t s);
+cudaError_t launch_fill_full(unsigned char *mult, unsigned char *cls, long long ncell, cudaStream_t s);
+cudaError_t launch_bits_to_cells(const uint32_t *bits, int nx, int ny, unsigned char *mult,
+                                 unsigned char *cls, cudaStream_t s);
+// xyT: 3N doubles on the device: cx[N], cy[N], T[N]. removed: one unsigned long long.
+cudaError_t launch_remove_covered(unsigned char *mult, const GridDesc &g, const double *xyT, int N,
+                                  unsigned long long *removed, cudaStream_t s);
+cudaError_t launch_covered_mask(unsigned char *mask, const GridDesc &g, const double *xyT, int N,
+                                cudaStream_t s);
+cudaError_t launch_thresholds(const double *xyR, int N, double *xyT, cudaStream_t s);
+cudaError_t launch_add_points(unsigned char *mult, unsigned char *cls, const int *cell_idx,
+                              const unsigned char *cell_cls, long long P, int *overflow, cudaStream_t s);
+cudaError_t launch_argmin(const double *obj, const unsigned char *feasible, long long B, int barrier,
+                          double *scratch_obj, long long *scratch_idx, int scratch_n, cudaStream_t s);
+cudaError_t launch_generate(double *dX, long long B, int N, unsigned long long seed, long long first,
+                            double lx, double ly, double h_min, double h_max, double tan_half_fov,
+                            cudaStream_t s);
+
+} // namespace cov

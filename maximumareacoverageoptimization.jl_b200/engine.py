@@ -1,0 +1,292 @@
+"""CoverageEngine -- a thin object wrapper over one libcoverage_cuda handle (one GPU, one stream).
+
+All coverage arithmetic happens in the CUDA kernels behind the C ABI (include/coverage_cuda.h);
+this class only marshals NumPy buffers.  Citations are relative to /root/reference/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from ._lib import CoverageError, lib
+
+TAN_HALF_FOV_DEFAULT = math.tan((100 / 180 * math.pi) / 2)  # FOV = 100/180*pi, src/FullSimulation.jl:735
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+class PinnedArray:
+    """A NumPy view over pinned host memory obtained from cov_host_alloc (freed with the engine
+    or explicitly).  cov_eval_batch DMA-copies pinned buffers in place, without staging."""
+
+    def __init__(self, engine: "CoverageEngine", shape, dtype):
+        self._engine = engine
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = C.c_void_p()
+        engine._check(lib.cov_host_alloc(engine._h, max(n, 1), C.byref(p)))
+        self._p = p
+        buf = (C.c_char * max(n, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self._p is not None and self._engine._h is not None:
+            self.array = None
+            lib.cov_host_free(self._engine._h, self._p)
+        self._p = None
+
+
+class CoverageEngine:
+    """One device-resident cell store + closure parameters + evaluation entry points."""
+
+    def __init__(self, device: int = 0):
+        self._h = None
+        h = C.c_void_p()
+        rc = lib.cov_create(int(device), C.byref(h))
+        if rc != _lib.COV_OK:
+            raise CoverageError(rc, lib.cov_last_error(None).decode())
+        self._h = h
+        self.device = int(device)
+        self.N = None
+        self._pinned = []
+
+    # ---- plumbing ----
+    def _check(self, rc: int):
+        if rc != _lib.COV_OK:
+            raise CoverageError(rc, lib.cov_last_error(self._h).decode())
+
+    def close(self):
+        if self._h is not None:
+            for p in self._pinned:
+                p.free()
+            self._pinned = []
+            lib.cov_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def handle(self):
+        return self._h
+
+    def set_option(self, option: int, value: int):
+        self._check(lib.cov_set_option(self._h, option, int(value)))
+
+    def get_option(self, option: int) -> int:
+        v = C.c_int64()
+        self._check(lib.cov_get_option(self._h, option, C.byref(v)))
+        return v.value
+
+    def pinned(self, shape, dtype=np.float64) -> np.ndarray:
+        p = PinnedArray(self, shape, dtype)
+        self._pinned.append(p)
+        return p.array
+
+    # ---- cell store ----
+    def set_grid_bits(self, bits: np.ndarray, nx: int, ny: int, dx: float, dy: float, weight=None):
+        """bits: (ny, ceil(nx/32)) uint32; bit b of word w of row j-1 is cell i = 32w+b+1."""
+        bits = np.ascontiguousarray(bits, dtype=np.uint32)
+        if bits.size != ny * ((nx + 31) // 32):
+            raise ValueError("bits must hold ny * ceil(nx/32) words")
+        w = dx * dy if weight is None else weight
+        self._check(lib.cov_set_grid_bits(self._h, nx, ny, dx, dy, _ptr(bits), w))
+
+    def set_grid_cells(self, mult: np.ndarray, nx: int, ny: int, dx: float, dy: float, cls=None,
+                       class_weight=None):
+        """mult/cls: nx*ny bytes indexed (i-1) + nx*(j-1)."""
+        mult = np.ascontiguousarray(mult, dtype=np.uint8).ravel()
+        if mult.size != nx * ny:
+            raise ValueError("mult must hold nx*ny bytes")
+        if cls is not None:
+            cls = np.ascontiguousarray(cls, dtype=np.uint8).ravel()
+            if cls.size != nx * ny:
+                raise ValueError("cls must hold nx*ny bytes")
+        cw = _f64([dx * dy] if class_weight is None else class_weight)
+        self._check(lib.cov_set_grid_cells(self._h, nx, ny, dx, dy, _ptr(mult), _ptr(cls), cw.size, _ptr(cw)))
+
+    def set_grid_full(self, nx: int, ny: int, dx: float, dy: float):
+        """createPOI(dx, dy, nx, ny) on the device (src/AreaCoverageCalculation.jl:11-21)."""
+        self._check(lib.cov_set_grid_full(self._h, nx, ny, dx, dy))
+
+    def set_points(self, pts5: np.ndarray, nx: int, ny: int, dx: float, dy: float):
+        """The reference's own list layout: P x 5 [x, y, area, weight, covered]."""
+        pts5 = _f64(pts5).reshape(-1, 5)
+        self._check(lib.cov_set_points(self._h, _ptr(pts5), pts5.shape[0], nx, ny, dx, dy))
+
+    def add_points(self, pts5: np.ndarray):
+        pts5 = _f64(pts5).reshape(-1, 5)
+        self._check(lib.cov_add_points(self._h, _ptr(pts5), pts5.shape[0]))
+
+    def grid_info(self) -> dict:
+        gi = _lib.GridInfo()
+        self._check(lib.cov_get_grid_info(self._h, C.byref(gi)))
+        return {f: getattr(gi, f) for f, _ in _lib.GridInfo._fields_}
+
+    def grid_cells(self) -> np.ndarray:
+        gi = self.grid_info()
+        out = np.empty(gi["nx"] * gi["ny"], dtype=np.uint8)
+        self._check(lib.cov_get_grid_cells(self._h, _ptr(out)))
+        return out
+
+    def remove_covered(self, xyR) -> int:
+        """rmvCoveredPOI (src/CellFunctions.jl:81-108) on the device-resident store."""
+        xyR = _f64(xyR).ravel()
+        removed = C.c_int64()
+        self._check(lib.cov_remove_covered(self._h, _ptr(xyR), xyR.size // 3, C.byref(removed)))
+        return removed.value
+
+    def covered_mask(self, x) -> np.ndarray:
+        x = _f64(x).ravel()
+        gi = self.grid_info()
+        out = np.empty(gi["nx"] * gi["ny"], dtype=np.uint8)
+        self._check(lib.cov_covered_mask(self._h, _ptr(x), _ptr(out)))
+        return out
+
+    # ---- parameters ----
+    def set_params(self, N: int, r_max, penalty_scale: float = 1e5, prev_xyR=None, d_lim=None,
+                   tan_half_fov: float = TAN_HALF_FOV_DEFAULT, sep_min: float = 0.0, use_cons7: bool = False):
+        r_max = _f64(r_max).ravel()
+        if r_max.size != N:
+            raise ValueError("r_max must have N entries")
+        if prev_xyR is not None:
+            prev_xyR = _f64(prev_xyR).ravel()
+            if prev_xyR.size != 3 * N:
+                raise ValueError("prev_xyR must have 3N entries")
+            d_lim = _f64(np.broadcast_to(np.asarray(d_lim, dtype=np.float64), (N,)))
+        self._check(lib.cov_set_params(self._h, N, _ptr(r_max), penalty_scale, _ptr(prev_xyR),
+                                       _ptr(d_lim) if prev_xyR is not None else None, tan_half_fov,
+                                       float(sep_min), 1 if use_cons7 else 0))
+        self.N = int(N)
+
+    # ---- evaluation ----
+    def eval_batch(self, X, want_count=True, want_feasible=True, want_class_count=False,
+                   want_progressive=False, out=None):
+        """X: (B, 3N) float64, rows [x;y;R].  Returns dict(obj, count, feasible, ...)."""
+        X = _f64(X)
+        if X.ndim == 1:
+            X = X.reshape(1, -1)
+        if self.N is None or X.shape[1] != 3 * self.N:
+            raise ValueError("X must be (B, 3N) with the N given to set_params")
+        B = X.shape[0]
+        res = out if out is not None else {}
+        if "obj" not in res:
+            res["obj"] = np.empty(B, dtype=np.float64)
+        if want_count and "count" not in res:
+            res["count"] = np.empty(B, dtype=np.int64)
+        if want_feasible and "feasible" not in res:
+            res["feasible"] = np.empty(B, dtype=np.uint8)
+        if want_class_count or want_progressive:
+            ncls = self.grid_info()["n_classes"]
+            if want_class_count and "class_count" not in res:
+                res["class_count"] = np.empty((B, ncls), dtype=np.int64)
+            if want_progressive and "progressive" not in res:
+                res["progressive"] = np.empty(B, dtype=np.float64)
+            self._check(lib.cov_eval_batch_ex(self._h, _ptr(X), B, _ptr(res["obj"]), _ptr(res.get("count")),
+                                              _ptr(res.get("feasible")), _ptr(res.get("class_count")),
+                                              _ptr(res.get("progressive"))))
+        else:
+            self._check(lib.cov_eval_batch(self._h, _ptr(X), B, _ptr(res["obj"]), _ptr(res.get("count")),
+                                           _ptr(res.get("feasible"))))
+        return res
+
+    def eval_one(self, x) -> float:
+        """AreaMaxObjective(x) for one candidate (src/TDM_STATIC_opt.jl:83-98)."""
+        x = _f64(x).ravel()
+        if self.N is None or x.size != 3 * self.N:
+            raise ValueError("x must have 3N entries")
+        v = C.c_double()
+        self._check(lib.cov_eval_one(self._h, _ptr(x), C.byref(v)))
+        return v.value
+
+    def argmin(self, X, barrier: bool = True):
+        X = _f64(X)
+        if X.ndim == 1:
+            X = X.reshape(1, -1)
+        bo, bi = C.c_double(), C.c_int64()
+        self._check(lib.cov_argmin(self._h, _ptr(X), X.shape[0], 1 if barrier else 0, C.byref(bo), C.byref(bi)))
+        return bo.value, bi.value
+
+    def eval_batch_device(self, dX: int, B: int, d_obj: int, d_count: int = 0, d_feasible: int = 0):
+        """Device pointers (ints); asynchronous on the engine's stream."""
+        self._check(lib.cov_eval_batch_device(self._h, C.c_void_p(dX), B, C.c_void_p(d_obj),
+                                              C.c_void_p(d_count) if d_count else None,
+                                              C.c_void_p(d_feasible) if d_feasible else None))
+
+    def generate_candidates(self, dX: int, B: int, N: int, seed: int, first_index: int = 0, lx=500.0, ly=500.0,
+                            h_min=5.0, h_max=30.0, tan_half_fov=TAN_HALF_FOV_DEFAULT):
+        self._check(lib.cov_generate_candidates(self._h, C.c_void_p(dX), B, N, seed, first_index, lx, ly, h_min,
+                                                h_max, tan_half_fov))
+
+    def device_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._check(lib.cov_device_alloc(self._h, nbytes, C.byref(p)))
+        return p.value
+
+    def device_free(self, p: int):
+        self._check(lib.cov_device_free(self._h, C.c_void_p(p)))
+
+    def memcpy_h2d(self, dst: int, src: np.ndarray):
+        self._check(lib.cov_memcpy_h2d(self._h, C.c_void_p(dst), _ptr(src), src.nbytes))
+
+    def memcpy_d2h(self, dst: np.ndarray, src: int):
+        self._check(lib.cov_memcpy_d2h(self._h, _ptr(dst), C.c_void_p(src), dst.nbytes))
+
+    def sync(self):
+        self._check(lib.cov_sync(self._h))
+
+    def stream(self) -> int:
+        return lib.cov_stream(self._h) or 0
+
+    def set_stream(self, stream: int):
+        self._check(lib.cov_set_stream(self._h, C.c_void_p(stream) if stream else None))
+
+    def launch_count(self) -> int:
+        return lib.cov_launch_count(self._h)
+
+    def last_kernel_ms(self) -> float:
+        v = C.c_double()
+        self._check(lib.cov_last_kernel_ms(self._h, C.byref(v)))
+        return v.value
+
+    def kernel_time_total(self):
+        """(summed coverage-kernel device time in ms, launches) since the engine was created."""
+        ms, n = C.c_double(), C.c_int64()
+        self._check(lib.cov_kernel_time_total(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+
+def threshold(R: float) -> float:
+    """T(R): sqrt(s) < R  <=>  s < T(R) (the closed form the kernels use)."""
+    return lib.cov_threshold(float(R))
+
+
+def limits() -> dict:
+    lim = _lib.Limits()
+    lib.cov_get_limits(C.byref(lim))
+    return {f: getattr(lim, f) for f, _ in _lib.Limits._fields_}
+
+
+def device_count() -> int:
+    return lib.cov_device_count()

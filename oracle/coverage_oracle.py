@@ -1,0 +1,172 @@
+"""NumPy restatement of the reference's coverage-objective path, written independently of
+coverage_oracle.c so the two can check each other.
+
+TEST INFRASTRUCTURE ONLY -- nothing in the product imports this module (see oracle/README.md).
+
+PARITY UNPINNED: the reference is Julia, Julia is not installed, and the reference's own test
+suite (test/runtests.jl:1-6) holds no vectors for this path.  Every function cites the Julia
+lines it restates; citations are relative to /root/reference/.
+
+NumPy float64 ufuncs are IEEE-754 binary64, round-to-nearest, and `a*a + b*b` is evaluated as
+separate multiply/add ufunc calls, so no FMA contraction can occur -- the same arithmetic as
+Julia's `sqrt((px-cx)^2 + (py-cy)^2) < R`.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+TAN_HALF_FOV_DEFAULT = math.tan((100 / 180 * math.pi) / 2)  # src/FullSimulation.jl:735
+
+
+def createPOI(dx: float, dy: float, x_length: float, y_length: float) -> np.ndarray:
+    """src/AreaCoverageCalculation.jl:11-21 -- i outer, j inner; returns P x 5 float64."""
+    i = np.arange(1.0, math.floor(x_length) + 1.0)
+    j = np.arange(1.0, math.floor(y_length) + 1.0)
+    px = i * dx - dx / 2
+    py = j * dy - dy / 2
+    pts = np.empty((len(i) * len(j), 5), dtype=np.float64)
+    pts[:, 0] = np.repeat(px, len(j))
+    pts[:, 1] = np.tile(py, len(i))
+    pts[:, 2] = dx * dy
+    pts[:, 3] = dx * dy
+    pts[:, 4] = 0.0
+    return pts
+
+
+def make_circles(arr):
+    """src/AreaCoverageCalculation.jl:33-45 -- [x;y;R] -> list of (x, y, R)."""
+    arr = np.asarray(arr, dtype=np.float64)
+    n = len(arr) // 3
+    return [(arr[i], arr[n + i], arr[2 * n + i]) for i in range(n)]
+
+
+def make_MADS(circles) -> np.ndarray:
+    """src/AreaCoverageCalculation.jl:48-59 -- list of (x, y, R) -> [x;y;R]."""
+    return np.array([c[0] for c in circles] + [c[1] for c in circles] + [c[2] for c in circles],
+                    dtype=np.float64)
+
+
+def covered_mask(circles, pts: np.ndarray) -> np.ndarray:
+    """Boolean per list entry: covered by ANY disc (the first-hit `break` only decides which
+    disc claims the point, not whether it is counted).  Predicate of
+    src/AreaCoverageCalculation.jl:70."""
+    circles = np.asarray(circles, dtype=np.float64)
+    n = len(circles) // 3
+    px = pts[:, 0]
+    py = pts[:, 1]
+    cov = np.zeros(len(pts), dtype=bool)
+    for c in range(n):
+        ddx = px - circles[c]
+        ddy = py - circles[n + c]
+        s = ddx * ddx + ddy * ddy
+        with np.errstate(invalid="ignore"):
+            cov |= np.sqrt(s) < circles[2 * n + c]
+    return cov
+
+
+def calculateArea(circles, pts: np.ndarray):
+    """src/AreaCoverageCalculation.jl:63-110 -- returns (area, count).  The area is the
+    sequential Float64 sum of the covered entries' weights in list order (np.cumsum is a
+    strictly sequential accumulation, unlike np.sum's pairwise scheme)."""
+    cov = covered_mask(circles, pts)
+    w = pts[cov, 3]
+    area = float(np.cumsum(w)[-1]) if len(w) else 0.0
+    return area, int(cov.sum())
+
+
+def objective(x, pts: np.ndarray, N: int, r_max):
+    """src/TDM_STATIC_opt.jl:82-100 -- returns (objective, count)."""
+    x = np.asarray(x, dtype=np.float64)
+    r_max = np.asarray(r_max, dtype=np.float64)
+    area, count = calculateArea(x, pts)
+    violation = 0.0
+    for i in range(N):
+        violation += abs(float(x[i + 2 * N]) - float(r_max[i]))
+    return -area + violation * 1e5, count
+
+
+def cons3(x, pre, tan_half_fov: float, d_lim) -> bool:
+    """src/TDM_Constraints.jl:54-75."""
+    x = np.asarray(x, dtype=np.float64)
+    pre = np.asarray(pre, dtype=np.float64)
+    n = len(x) // 3
+    for i in range(n):
+        z1 = float(pre[2 * n + i]) / tan_half_fov
+        z2 = float(x[2 * n + i]) / tan_half_fov
+        ax = float(pre[i]) - float(x[i])
+        ay = float(pre[n + i]) - float(x[n + i])
+        az = z1 - z2
+        if math.sqrt(ax * ax + ay * ay + az * az) > float(d_lim[i]):
+            return False
+    return True
+
+
+def cons7(x, tan_half_fov: float) -> bool:
+    """src/TDM_Constraints.jl:142-154."""
+    x = np.asarray(x, dtype=np.float64)
+    n = len(x) // 3
+    for i in range(n):
+        if x[i + n] < 200 and x[i + 2 * n] > 19 * tan_half_fov:
+            return False
+    return True
+
+
+def cons8(x, sep: float = 15.0) -> bool:
+    """src/TDM_Constraints.jl:157-172."""
+    x = np.asarray(x, dtype=np.float64)
+    n = len(x) // 3
+    for i in range(n):
+        for j in range(n):
+            if j != i:
+                ax = float(x[i]) - float(x[j])
+                ay = float(x[i + n]) - float(x[j + n])
+                if math.sqrt(ax * ax + ay * ay) < sep:
+                    return False
+    return True
+
+
+def cons1_progressive(x, r_max) -> float:
+    """src/TDM_Constraints.jl:182-195."""
+    x = np.asarray(x, dtype=np.float64)
+    n = len(x) // 3
+    violation = 0.0
+    for i in range(n):
+        violation += max(float(x[2 * n + i]) - float(r_max[i]), 0.0)
+    return violation
+
+
+def rmvCoveredPOI(circles, pts: np.ndarray) -> np.ndarray:
+    """src/CellFunctions.jl:81-108 -- returns the surviving points in list order."""
+    return pts[~covered_mask(circles, pts)]
+
+
+def allocate_even_circles(r_centering_cir: float, N: int, r_uav: float, center_x: float,
+                          center_y: float) -> np.ndarray:
+    """src/Base_Functions.jl:44-65."""
+    xs, ys, rs = [], [], []
+    for i in range(1, N + 1):
+        ref_angle = 2 * math.pi / N * (i - 1)
+        xs.append(r_centering_cir * math.cos(ref_angle) + center_x)
+        ys.append(r_centering_cir * math.sin(ref_angle) + center_y)
+        rs.append(r_uav)
+    return np.array(xs + ys + rs, dtype=np.float64)
+
+
+def threshold_by_search(R: float) -> float:
+    """T(R) = smallest double t with sqrt(t) >= R (see coverage_oracle.c)."""
+    if not (R > 0):
+        return 0.0
+    if math.isinf(R):
+        return math.inf
+    t = R * R
+    if math.isinf(t):
+        t = 1.7976931348623157e308
+        if math.sqrt(t) < R:
+            return math.inf
+    while t > 0 and math.sqrt(t) >= R:
+        t = math.nextafter(t, -math.inf)
+    while math.sqrt(t) < R:
+        t = math.nextafter(t, math.inf)
+    return t

@@ -1,0 +1,554 @@
+"""GPU parity tests: libcoverage_cuda (through its C ABI, via ctypes) against the CPU oracle on the
+same seeded inputs, the golden vectors, and size-independent properties at BASELINE's sizes.
+Integer counts, feasibility flags and Float64 objectives are compared BIT-EXACTLY."""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+T = math.tan((100 / 180 * math.pi) / 2)
+KERNELS = {"span": 1, "brute": 2, "exact": 3}
+
+
+def rand_candidates(rng, B, N, extent=500.0, hmin=5.0, hmax=30.0):
+    return np.concatenate([rng.random((B, 2 * N)) * extent, (hmin + rng.random((B, N)) * (hmax - hmin)) * T], axis=1)
+
+
+def check_against_oracle(cov, orc, eng, X, N, r_max, pts, **cons):
+    want = orc.eval_batch(X, N, r_max, pts, want_prog=True, **cons)
+    got = eng.eval_batch(X, want_progressive=True)
+    assert np.array_equal(got["count"], want["count"]), np.flatnonzero(got["count"] != want["count"])[:10]
+    assert np.array_equal(got["feasible"], want["feasible"])
+    assert np.array_equal(got["obj"].view(np.uint64), want["obj"].view(np.uint64))
+    assert np.array_equal(got["progressive"].view(np.uint64), want["progressive"].view(np.uint64))
+    return got
+
+
+# ---------------------------------------------------------------- golden vectors
+def test_kat_static_grid(cov, orc, engine, kat):
+    engine.set_grid_full(100, 100, 5.0, 5.0)
+    info = engine.grid_info()
+    assert (info["n_entries"], info["n_cells"], info["n_planes"], info["area_exact"]) == (10000, 10000, 1, 1)
+    engine.set_params(1, [0.0], penalty_scale=0.0)
+    for k in kat["kat2"]:
+        r = engine.eval_batch(np.array([k["disc"]]))
+        assert r["count"][0] == k["count"] and r["obj"][0] == -k["area"]
+    r_max = np.array(kat["kat3"]["r_max"])
+    engine.set_params(5, r_max)
+    for name in ("kat3", "kat4"):
+        k = kat[name]
+        r = engine.eval_batch(np.array([k["x"]]))
+        assert r["count"][0] == k["count"] and r["obj"][0] == k["objective"]
+        assert engine.eval_one(k["x"]) == k["objective"]
+
+
+def test_kat_static_grid_from_list(cov, orc, engine, kat):
+    """Same vectors with the store built from the reference's own list layout (cov_set_points)."""
+    pts = orc.createPOI(5.0, 5.0, 100.0, 100.0)
+    engine.set_points(pts, 100, 100, 5.0, 5.0)
+    engine.set_params(5, kat["kat3"]["r_max"])
+    X = np.array([kat["kat3"]["x"], kat["kat4"]["x"]])
+    r = engine.eval_batch(X)
+    assert r["count"].tolist() == [kat["kat3"]["count"], kat["kat4"]["count"]]
+    assert r["obj"].tolist() == [kat["kat3"]["objective"], kat["kat4"]["objective"]]
+
+
+def test_kat5_fire_list_multiplicities(cov, orc, engine, fire_rows, kat):
+    k = kat["kat5"]
+    allp = np.concatenate(fire_rows)
+    engine.set_points(allp, 100, 100, 5.0, 5.0)
+    info = engine.grid_info()
+    assert (info["n_entries"], info["n_cells"]) == (k["entries"], k["unique"])
+    assert info["n_planes"] == 2  # multiplicities 1..3 -> two bit planes
+    mult = engine.grid_cells()
+    assert np.bincount(mult)[1:].tolist() == [k["mult_hist"][str(m)] for m in (1, 2, 3)]
+    engine.set_params(1, [0.0], penalty_scale=0.0)
+    r = engine.eval_batch(np.array([k["all_covering_disc"]]))
+    assert r["count"][0] == k["entries"] and r["obj"][0] == -25.0 * k["entries"]
+    rng = np.random.default_rng(5)
+    N = 5
+    engine.set_params(N, np.full(N, 30 * T))
+    X = rand_candidates(rng, 3000, N)
+    X[:, N:2 * N] *= 0.75  # the fire sits at y < 355
+    for name, kid in KERNELS.items():
+        engine.set_option(cov.OPT_KERNEL, kid)
+        got = check_against_oracle(cov, orc, engine, X, N, np.full(N, 30 * T), allp)
+    assert got["count"].max() > 50
+
+
+def test_recorded_targets(cov, orc, engine, targets):
+    """Quadrotor_Targets.xlsx: recorded integer-valued MADS inputs of UAV 1 (x, y, z = R/tan)."""
+    pts = orc.createPOI(5.0, 5.0, 100.0, 100.0)
+    engine.set_grid_full(100, 100, 5.0, 5.0)
+    for key in ("root", "src"):
+        t = targets[key]
+        X = np.stack([t[:, 0], t[:, 1], t[:, 2] * T], axis=1)
+        engine.set_params(1, [30 * T])
+        check_against_oracle(cov, orc, engine, X, 1, [30 * T], pts)
+
+
+# ---------------------------------------------------------------- randomised differential tests
+@pytest.mark.parametrize("kernel", list(KERNELS))
+@pytest.mark.parametrize("force_exact", [0, 1])
+def test_c1_random_vs_oracle(cov, orc, engine, kernel, force_exact):
+    if kernel == "exact" and force_exact:
+        pytest.skip("exact kernel has no FP32 stage")
+    rng = np.random.default_rng(100 + force_exact)
+    pts = orc.createPOI(5.0, 5.0, 100.0, 100.0)
+    engine.set_grid_full(100, 100, 5.0, 5.0)
+    engine.set_option(cov.OPT_KERNEL, KERNELS[kernel])
+    engine.set_option(cov.OPT_FORCE_EXACT, force_exact)
+    N = 5
+    r_max = np.full(N, 30 * T)
+    X = rand_candidates(rng, 1500, N)
+    X[:200] = np.rint(X[:200])           # integer mesh (granularity 1.0) -> many exact ties
+    X[200:300, :2 * N] = np.rint(X[200:300, :2 * N] / 2.5) * 2.5  # centres on cell corners / centres
+    X[200:300, 2 * N:] = np.rint(X[200:300, 2 * N:] / 2.5) * 2.5
+    pre = X[7].copy()
+    X[300:600] = pre + rng.normal(0, 4.0, (300, 3 * N))  # around the previous state: cons3 both ways
+    engine.set_params(N, r_max, prev_xyR=pre, d_lim=10.0, tan_half_fov=T, sep_min=15.0, use_cons7=True)
+    got = check_against_oracle(cov, orc, engine, X, N, r_max, pts, pre=pre, d_lim=10.0, tan_half_fov=T,
+                               sep_min=15.0, use_cons7=True)
+    assert 0 < got["feasible"].sum() < len(X)
+
+
+def test_c2_fire_grid_vs_oracle(cov, orc, engine):
+    n = 256
+    d = 500.0 / n
+    bits, nset = cov.synth.fire_grid(n)
+    pts = cov.synth.points_from_bits(bits, n, d, d)
+    assert len(pts) == nset
+    engine.set_grid_bits(bits, n, n, d, d)
+    assert engine.grid_info()["n_entries"] == nset
+    N = 5
+    r_max = np.full(N, 30 * T)
+    engine.set_params(N, r_max)
+    X = cov.synth.random_candidates(4096, N, seed=1)
+    for name, kid in KERNELS.items():
+        engine.set_option(cov.OPT_KERNEL, kid)
+        check_against_oracle(cov, orc, engine, X[:4096 if name != "exact" else 512], N, r_max, pts)
+
+
+def test_c3_shape_vs_oracle(cov, orc, engine):
+    n = 1024
+    d = 500.0 / n
+    bits, nset = cov.synth.fire_grid(n)
+    pts = cov.synth.points_from_bits(bits, n, d, d)
+    engine.set_grid_bits(bits, n, n, d, d)
+    N = 50
+    r_max = np.full(N, 30 * T)
+    engine.set_params(N, r_max, sep_min=15.0)
+    X = cov.synth.random_candidates(96, N, seed=2)
+    X[:8, :2 * N] = 100 + X[:8, :2 * N] * 0.1  # a tight swarm: heavy overlap, cons8 violated
+    got = check_against_oracle(cov, orc, engine, X, N, r_max, pts, sep_min=15.0)
+    engine.set_option(cov.OPT_KERNEL, KERNELS["brute"])
+    check_against_oracle(cov, orc, engine, X[:32], N, r_max, pts, sep_min=15.0)
+    assert got["count"].max() > 1000
+
+
+def test_c4_shape_vs_oracle(cov, orc, engine):
+    n = 4096
+    d = 500.0 / n
+    bits, nset = cov.synth.fire_grid(n)
+    pts = cov.synth.points_from_bits(bits, n, d, d)
+    engine.set_grid_bits(bits, n, n, d, d)
+    N = 200
+    r_max = np.full(N, 30 * T)
+    engine.set_params(N, r_max, sep_min=15.0)
+    X = cov.synth.random_candidates(6, N, seed=3)
+    check_against_oracle(cov, orc, engine, X, N, r_max, pts, sep_min=15.0)
+
+
+def test_near_boundary_adversarial(cov, orc, engine):
+    """Centres placed so that the radicand of some cell is within a few ulps of T(R)."""
+    rng = np.random.default_rng(42)
+    n, d = 64, 500.0 / 64
+    pts = orc.createPOI(d, d, float(n), float(n))
+    engine.set_grid_full(n, n, d, d)
+    rows = []
+    for _ in range(1500):
+        i, j = rng.integers(1, n + 1, 2)
+        px, py = i * d - d / 2, j * d - d / 2
+        R = float((5 + rng.random() * 25) * T) if rng.random() < 0.7 else float(rng.integers(4, 40))
+        th = rng.random() * 2 * math.pi if rng.random() < 0.6 else rng.choice([0, math.pi / 2, math.pi])
+        cx, cy = px - R * math.cos(th), py - R * math.sin(th)
+        for _ in range(int(rng.integers(0, 4))):
+            cx = math.nextafter(cx, cx + rng.choice([-1.0, 1.0]))
+        rows.append([cx, cy, R])
+    X = np.array(rows)
+    for kernel in ("span", "brute"):
+        for fe in (0, 1):
+            engine.set_option(cov.OPT_KERNEL, KERNELS[kernel])
+            engine.set_option(cov.OPT_FORCE_EXACT, fe)
+            engine.set_params(1, [30 * T])
+            check_against_oracle(cov, orc, engine, X, 1, [30 * T], pts)
+
+
+def test_non_f32_lattice_and_ragged_width(cov, orc, engine):
+    """dx = 0.1 (not exactly representable), nx = 77 (ragged last word), ny = 45."""
+    rng = np.random.default_rng(8)
+    nx, ny, dx, dy = 77, 45, 0.1, 0.3
+    fire = rng.random((nx, ny)) < 0.6
+    bits = cov.synth.pack_bits(fire)
+    pts = cov.synth.points_from_bits(bits, nx, dx, dy)
+    engine.set_grid_bits(bits, nx, ny, dx, dy)
+    N = 3
+    X = np.concatenate([rng.random((800, N)) * 9 - 0.6, rng.random((800, N)) * 15 - 0.8,
+                        rng.random((800, N)) * 2.5], axis=1)
+    r_max = np.full(N, 1.0)
+    for kernel in ("span", "brute", "exact"):
+        engine.set_option(cov.OPT_KERNEL, KERNELS[kernel])
+        engine.set_params(N, r_max)
+        check_against_oracle(cov, orc, engine, X, N, r_max, pts)
+
+
+# ---------------------------------------------------------------- edge cases
+def test_edge_radii_and_far_centres(cov, orc, engine):
+    pts = orc.createPOI(5.0, 5.0, 100.0, 100.0)
+    engine.set_grid_full(100, 100, 5.0, 5.0)
+    N = 2
+    r_max = np.full(N, 30 * T)
+    engine.set_params(N, r_max)
+    inf, nan = math.inf, math.nan
+    X = np.array([
+        [250, 250, 250, 250, 0.0, 0.0],            # R = 0: nothing covered
+        [250, 250, 250, 250, -5.0, -0.0],          # negative R
+        [250, 250, 250, 250, nan, 10.0],           # NaN R never covers, NaN penalty
+        [250, 250, 250, 250, inf, 1.0],            # infinite R covers everything
+        [-1e6, 250, 1e6, 250, 30.0, 30.0],         # far outside
+        [1e300, 250, 250, -1e300, 1e300, 20.0],    # huge coordinates and radius (overflowing squares)
+        [250, 1e18, 250, 250, 1e18, 3.0],          # absorption: |py - cy| rounds
+        [2.5, 497.5, 2.5, 497.5, 2.5, 2.6],        # corner cells
+        [250, 250, 250, 250, 1e-300, 5e-324],      # denormal radii
+        [nan, 250, 250, 250, 10.0, 10.0],          # NaN centre
+        [inf, 250, 250, 250, inf, 10.0],           # inf - inf = NaN in the radicand
+        [0, 500, 0, 500, 707.2, 1.0],              # everything within one disc
+    ], dtype=np.float64)
+    for kernel in ("span", "brute", "exact"):
+        engine.set_option(cov.OPT_KERNEL, KERNELS[kernel])
+        want = orc.eval_batch(X, N, r_max, pts)
+        got = engine.eval_batch(X)
+        assert np.array_equal(got["count"], want["count"]), (kernel, got["count"], want["count"])
+        assert np.array_equal(got["obj"].view(np.uint64) | (np.isnan(got["obj"]) * np.uint64(0)),
+                              want["obj"].view(np.uint64)) or (
+            np.array_equal(np.isnan(got["obj"]), np.isnan(want["obj"])) and
+            np.array_equal(got["obj"][~np.isnan(got["obj"])], want["obj"][~np.isnan(want["obj"])]))
+
+
+def test_empty_inputs(cov, orc, engine):
+    engine.set_points(np.zeros((0, 5)), 100, 100, 5.0, 5.0)
+    info = engine.grid_info()
+    assert info["n_entries"] == 0
+    engine.set_params(5, np.full(5, 30 * T))
+    X = cov.synth.random_candidates(64, 5, seed=4)
+    r = engine.eval_batch(X)
+    assert not r["count"].any()
+    want = orc.eval_batch(X, 5, np.full(5, 30 * T), np.zeros((0, 5)))
+    assert np.array_equal(r["obj"], want["obj"])
+    r0 = engine.eval_batch(np.zeros((0, 15)))
+    assert r0["obj"].shape == (0,)
+
+
+def test_state_and_argument_errors(cov, engine):
+    e = engine
+    e.N = 1
+    with pytest.raises(cov.CoverageError) as ei:
+        e.eval_batch(np.zeros((1, 3)))
+    assert ei.value.code == cov._lib.COV_ERR_STATE
+    e.set_grid_full(10, 10, 5.0, 5.0)
+    with pytest.raises(cov.CoverageError) as ei:
+        e.eval_batch(np.zeros((1, 3)))
+    assert ei.value.code == cov._lib.COV_ERR_STATE and "parameters" in ei.value.message
+    with pytest.raises(cov.CoverageError) as ei:
+        e.set_points(np.array([[2.6, 2.5, 25, 25, 0]]), 10, 10, 5.0, 5.0)
+    assert ei.value.code == cov._lib.COV_ERR_OFF_LATTICE
+    with pytest.raises(cov.CoverageError) as ei:
+        e.set_points(np.array([[52.5, 2.5, 25, 25, 0]]), 10, 10, 5.0, 5.0)  # outside the lattice
+    assert ei.value.code == cov._lib.COV_ERR_OFF_LATTICE
+    with pytest.raises(cov.CoverageError) as ei:
+        e.set_grid_full(0, 10, 5.0, 5.0)
+    assert ei.value.code == cov._lib.COV_ERR_INVALID
+    with pytest.raises(cov.CoverageError) as ei:
+        e.set_grid_full(40000, 10, 5.0, 5.0)
+    assert ei.value.code == cov._lib.COV_ERR_LIMIT
+    with pytest.raises(cov.CoverageError):
+        cov.CoverageEngine(9999)
+
+
+# ---------------------------------------------------------------- cell store operations
+def test_weight_classes_and_ordered_sum(cov, orc, engine, fire_rows):
+    """High-interest weights (src/CellFunctions.jl:41-45): per-class integer counts are exact; the
+    order-dependent Float64 area is replayed on the host from the device's covered mask."""
+    allp = np.concatenate(fire_rows[:30]).copy()
+    hi = (allp[:, 0] > 200) & (allp[:, 0] < 300) & (allp[:, 1] > 250)
+    allp[hi, 3] = (30.0 * T) ** 2 * math.pi
+    engine.set_points(allp, 100, 100, 5.0, 5.0)
+    info = engine.grid_info()
+    assert info["n_classes"] == 2 and info["area_exact"] == 0
+    N = 4
+    engine.set_params(N, np.full(N, 30 * T))
+    rng = np.random.default_rng(21)
+    X = rand_candidates(rng, 400, N)
+    X[:, N:2 * N] = 200 + X[:, N:2 * N] * 0.3
+    got = engine.eval_batch(X, want_class_count=True)
+    first_w = allp[0, 3]
+    class_of = (allp[:, 3] != first_w).astype(np.int32)
+    for b in range(0, 400, 7):
+        want = orc.class_counts(X[b], allp, class_of, 2)
+        assert got["class_count"][b].tolist() == want.tolist()
+    ACC = cov.AreaCoverageCalculation
+    pl = ACC.PointList(allp, 100, 100, 5.0, 5.0)
+    res = ACC.ResidentList(pl, engine=engine)
+    for b in range(0, 400, 23):
+        area, cnt, _ = orc.calculateArea(X[b], allp)
+        assert ACC.calculateArea(X[b], res) == area
+    obj = cov.TDM_STATIC_opt.createObjective(res, N, np.full(N, 30 * T))
+    for b in range(0, 400, 57):
+        assert obj(X[b]) == orc.objective(X[b], np.full(N, 30 * T), allp)[0]
+
+
+def test_remove_covered_and_add_points(cov, orc, engine, fire_rows):
+    pts = np.concatenate(fire_rows[:10])
+    engine.set_points(pts, 100, 100, 5.0, 5.0)
+    discs = np.array([220.0, 260.0, 345.0, 340.0, 12.0, 14.0])
+    want = orc.rmvCoveredPOI(discs, pts)
+    removed = engine.remove_covered(discs)
+    assert removed == len(pts) - len(want)
+    mult = engine.grid_cells()
+    ref = np.zeros(100 * 100, dtype=np.int64)
+    pl = cov.AreaCoverageCalculation.PointList(want, 100, 100, 5.0, 5.0)
+    np.add.at(ref, pl.cell_index(), 1)
+    assert np.array_equal(mult, ref)
+    engine.add_points(fire_rows[10])
+    ref2 = ref.copy()
+    np.add.at(ref2, cov.AreaCoverageCalculation.PointList(fire_rows[10], 100, 100, 5.0, 5.0).cell_index(), 1)
+    assert np.array_equal(engine.grid_cells(), ref2)
+    assert engine.grid_info()["n_entries"] == len(want) + len(fire_rows[10])
+    # and the objective sees the updated store
+    now = np.concatenate([want, fire_rows[10]])
+    N = 3
+    engine.set_params(N, np.full(N, 30 * T))
+    rng = np.random.default_rng(9)
+    X = rand_candidates(rng, 500, N)
+    X[:, N:2 * N] = 250 + X[:, N:2 * N] * 0.25
+    check_against_oracle(cov, orc, engine, X, N, np.full(N, 30 * T), now)
+
+
+def test_covered_mask(cov, orc, engine):
+    pts = orc.createPOI(5.0, 5.0, 100.0, 100.0)
+    engine.set_grid_full(100, 100, 5.0, 5.0)
+    engine.set_params(2, [0.0, 0.0])
+    x = np.array([100.3, 300.7, 200.1, 50.9, 33.3, 17.2])
+    mask = engine.covered_mask(x).astype(bool)
+    pl = cov.AreaCoverageCalculation.PointList(pts, 100, 100, 5.0, 5.0)
+    kept = orc.rmvCoveredPOI(x, pts)
+    assert (~mask[pl.cell_index()]).sum() == len(kept)
+
+
+def test_argmin_and_barrier(cov, orc, engine):
+    engine.set_grid_full(100, 100, 5.0, 5.0)
+    N = 5
+    r_max = np.full(N, 30 * T)
+    rng = np.random.default_rng(77)
+    pre = rand_candidates(rng, 1, N)[0]
+    X = pre + rng.normal(0, 3.5, (5000, 3 * N))
+    engine.set_params(N, r_max, prev_xyR=pre, d_lim=10.0, tan_half_fov=T)
+    r = engine.eval_batch(X)
+    feas = r["feasible"].astype(bool)
+    assert 0 < feas.sum() < len(X)
+    bo, bi = engine.argmin(X, barrier=True)
+    masked = np.where(feas, r["obj"], np.inf)
+    assert bi == int(np.argmin(masked)) and bo == masked[bi]
+    bo2, bi2 = engine.argmin(X, barrier=False)
+    assert bi2 == int(np.argmin(r["obj"])) and bo2 == r["obj"][bi2]
+    engine.set_params(N, r_max, prev_xyR=pre + 1000.0, d_lim=10.0, tan_half_fov=T)
+    bo3, bi3 = engine.argmin(X, barrier=True)
+    assert bi3 == -1 and bo3 == math.inf
+
+
+# ---------------------------------------------------------------- host-side mirror of the reference API
+def test_reference_api_static(cov, orc, kat):
+    CF, ACC, OPT, TC = cov.CellFunctions, cov.AreaCoverageCalculation, cov.TDM_STATIC_opt, cov.TDM_Constraints
+    cells = CF.initialise_POI(CF.Cells(), "static")
+    assert len(cells.points_of_interest) == 10000
+    r_max = np.array(kat["kat3"]["r_max"])
+    obj = OPT.createObjective(cells, 5, r_max)
+    assert obj(np.array(kat["kat3"]["x"])) == kat["kat3"]["objective"]
+    assert obj(np.array(kat["kat4"]["x"])) == kat["kat4"]["objective"]
+    assert ACC.calculateArea(np.array(kat["kat4"]["x"]), cells.points_of_interest) == kat["kat4"]["area"]
+    X = np.array([kat["kat3"]["x"], kat["kat4"]["x"]])
+    assert obj.batch(X).tolist() == [kat["kat3"]["objective"], kat["kat4"]["objective"]]
+    # r_max is captured by reference (mutated between timesteps, src/FullSimulation.jl:65-76)
+    r_max[0] = 15 * T
+    assert obj(np.array(kat["kat4"]["x"])) == orc.objective(kat["kat4"]["x"], r_max, cells.points_of_interest.data)[0]
+    # rmvCoveredPOI then the objective again
+    discs = np.array(kat["kat4"]["x"])
+    want = orc.rmvCoveredPOI(discs, cells.points_of_interest.data)
+    cells = CF.rmvCoveredPOI(cells, discs)
+    assert np.array_equal(cells.points_of_interest.data, want)
+    x5 = discs.copy()
+    x5[:5] += 20
+    assert obj(x5) == orc.objective(x5, r_max, want)[0]
+    # constraints
+    pre = ACC.make_circles(discs)
+    cons3 = TC.create_cons3(pre, 100 / 180 * math.pi, 10 * np.ones(5))
+    rng = np.random.default_rng(3)
+    Xc = discs + rng.normal(0, 4, (300, 15))
+    assert cons3.batch(Xc).tolist() == [orc.cons3(x, discs, T, np.full(5, 10.0)) for x in Xc]
+    assert cons3(discs) is True and TC.cons1(discs) is True
+    cons8 = TC.create_cons8(5)
+    assert cons8.batch(Xc).tolist() == [orc.cons8(x) for x in Xc]
+    cons7 = TC.create_cons7(5, 100 / 180 * math.pi)
+    Xc[:, 5:10] -= 60
+    assert cons7.batch(Xc).tolist() == [orc.cons7(x, T) for x in Xc]
+    prog = TC.create_cons1_progressive(5, r_max)
+    assert prog.batch(Xc).tolist() == [orc.cons1_progressive(x, r_max) for x in Xc]
+    # fused constraints
+    rest = obj.fuse([TC.cons1, cons3, lambda x: True])
+    assert len(rest) == 1
+    o, f = obj.batch(Xc, want_feasible=True)
+    assert f.tolist() == [orc.cons3(x, discs, T, np.full(5, 10.0)) for x in Xc]
+    cells.close()
+
+
+def test_reference_api_dynamic(cov, orc, fire_rows):
+    CF, OPT = cov.CellFunctions, cov.TDM_STATIC_opt
+    cells = CF.initialise_POI(CF.Cells(), "dynamic", fire_rows=fire_rows)
+    ref = np.concatenate(fire_rows[:10])
+    assert np.array_equal(cells.points_of_interest.data, ref)
+    N = 5
+    r_max = np.full(N, 30 * T)
+    rng = np.random.default_rng(31)
+    discs = np.concatenate([200 + rng.random(N) * 100, 300 + rng.random(N) * 50, np.full(N, 10 * T)])
+    for t in range(1, 8):
+        cells = CF.update_POI(cells, t)
+        if t != 1:
+            ref = np.concatenate([ref, fire_rows[t + 10 - 1]])
+        cells = CF.rmvCoveredPOI(cells, discs)
+        ref = orc.rmvCoveredPOI(discs, ref)
+        assert np.array_equal(cells.points_of_interest.data, ref)
+        obj = OPT.createObjective(cells, N, r_max)
+        X = discs + rng.normal(0, 6, (64, 3 * N))
+        want = orc.eval_batch(X, N, r_max, ref)["obj"]
+        assert np.array_equal(obj.batch(X), want)
+        assert obj(X[0]) == want[0]
+        discs = X[int(np.argmin(want))]
+    cells.close()
+
+
+# ---------------------------------------------------------------- device-resident path, pipeline, multi-GPU
+def test_device_path_and_generator(cov, orc, engine):
+    n = 256
+    d = 500.0 / n
+    bits, _ = cov.synth.fire_grid(n)
+    pts = cov.synth.points_from_bits(bits, n, d, d)
+    engine.set_grid_bits(bits, n, n, d, d)
+    N, B = 5, 5000
+    r_max = np.full(N, 30 * T)
+    engine.set_params(N, r_max)
+    dX = engine.device_alloc(B * 3 * N * 8)
+    d_obj, d_cnt, d_fe = engine.device_alloc(B * 8), engine.device_alloc(B * 8), engine.device_alloc(B)
+    engine.generate_candidates(dX, B, N, seed=2026, first_index=123456789012)
+    X = np.empty((B, 3 * N))
+    engine.memcpy_d2h(X, dX)
+    engine.sync()
+    assert np.array_equal(X, cov.synth.philox_candidates(B, N, 2026, 123456789012))
+    engine.eval_batch_device(dX, B, d_obj, d_cnt, d_fe)
+    obj, cnt = np.empty(B), np.empty(B, dtype=np.int64)
+    engine.memcpy_d2h(obj, d_obj)
+    engine.memcpy_d2h(cnt, d_cnt)
+    engine.sync()
+    assert engine.last_kernel_ms() > 0
+    want = orc.eval_batch(X, N, r_max, pts)
+    assert np.array_equal(cnt, want["count"]) and np.array_equal(obj, want["obj"])
+    for p in (dX, d_obj, d_cnt, d_fe):
+        engine.device_free(p)
+
+
+def test_host_pipeline_chunks_and_pinned(cov, orc, engine):
+    engine.set_grid_full(100, 100, 5.0, 5.0)
+    N, B = 5, 20000
+    r_max = np.full(N, 30 * T)
+    engine.set_params(N, r_max)
+    X = cov.synth.random_candidates(B, N, seed=5)
+    base = engine.eval_batch(X)
+    for chunk in (1, 999, 4096):
+        if chunk == 1:
+            sub = engine.eval_batch(X[:50])
+            engine.set_option(cov.OPT_CHUNK, 1)
+            r = engine.eval_batch(X[:50])
+            assert np.array_equal(r["obj"], sub["obj"])
+            continue
+        engine.set_option(cov.OPT_CHUNK, chunk)
+        r = engine.eval_batch(X)
+        for k in ("obj", "count", "feasible"):
+            assert np.array_equal(r[k], base[k])
+    Xp = engine.pinned((B, 3 * N))
+    Xp[:] = X
+    out = {"obj": engine.pinned((B,)), "count": engine.pinned((B,), np.int64), "feasible": engine.pinned((B,), np.uint8)}
+    r = engine.eval_batch(Xp, out=out)
+    for k in ("obj", "count", "feasible"):
+        assert np.array_equal(r[k], base[k])
+    sample = orc.eval_batch(X[:300], N, r_max, orc.createPOI(5.0, 5.0, 100.0, 100.0))
+    assert np.array_equal(base["obj"][:300], sample["obj"])
+
+
+def test_multi_shards_on_one_device(cov, orc):
+    """cov_multi with two handles on device 0: contiguous shards, host gather."""
+    import ctypes as C
+    lib = cov._lib.lib
+    devs = (C.c_int * 2)(0, 0)
+    m = C.c_void_p()
+    assert lib.cov_multi_create(devs, 2, C.byref(m)) == 0
+    try:
+        N, B = 5, 3001
+        r_max = np.full(N, 30 * T)
+        for k in range(lib.cov_multi_size(m)):
+            h = lib.cov_multi_handle(m, k)
+            assert lib.cov_set_grid_full(h, 100, 100, 5.0, 5.0) == 0
+            assert lib.cov_set_params(h, N, r_max.ctypes.data, 1e5, None, None, T, 0.0, 0) == 0
+        X = cov.synth.random_candidates(B, N, seed=6)
+        obj, cnt, fe = np.empty(B), np.empty(B, dtype=np.int64), np.empty(B, dtype=np.uint8)
+        assert lib.cov_multi_eval_batch(m, X.ctypes.data, B, obj.ctypes.data, cnt.ctypes.data, fe.ctypes.data) == 0
+        want = orc.eval_batch(X, N, r_max, orc.createPOI(5.0, 5.0, 100.0, 100.0))
+        assert np.array_equal(obj, want["obj"]) and np.array_equal(cnt, want["count"])
+        bo, bi = C.c_double(), C.c_int64()
+        assert lib.cov_multi_argmin(m, X.ctypes.data, B, 1, C.byref(bo), C.byref(bi)) == 0
+        assert bi.value == int(np.argmin(obj)) and bo.value == obj.min()
+    finally:
+        lib.cov_multi_destroy(m)
+
+
+# ---------------------------------------------------------------- size-independent properties at BASELINE sizes
+def test_full_c2_properties(cov, orc, engine):
+    """1 M candidates x 5 UAVs on the 256 x 256 fire grid: (1) the objective is invariant under a
+    permutation of the UAVs' discs except for the order-dependent penalty sum, whose terms we
+    permute consistently so it is identical too when r_max is uniform and the sum is exact...
+    we compare counts; (2) obj == -w*count + 1e5*violation recomputed in NumPy; (3) the span and
+    brute kernels agree on the whole batch; (4) a 2000-candidate sample equals the oracle."""
+    n = 256
+    d = 500.0 / n
+    bits, _ = cov.synth.fire_grid(n)
+    pts = cov.synth.points_from_bits(bits, n, d, d)
+    engine.set_grid_bits(bits, n, n, d, d)
+    N, B = 5, 1_000_000
+    r_max = np.full(N, 30 * T)
+    engine.set_params(N, r_max)
+    X = cov.synth.random_candidates(B, N, seed=1)
+    a = engine.eval_batch(X)
+    perm = np.array([3, 0, 4, 1, 2])
+    Xp = np.concatenate([X[:, perm], X[:, N + perm], X[:, 2 * N + perm]], axis=1)
+    b = engine.eval_batch(Xp)
+    assert np.array_equal(a["count"], b["count"])
+    viol = np.zeros(B)
+    for i in range(N):
+        viol = viol + np.abs(X[:, 2 * N + i] - r_max[i])
+    assert np.array_equal(a["obj"], -(d * d * a["count"].astype(np.float64)) + viol * 1e5)
+    engine.set_option(cov.OPT_KERNEL, KERNELS["brute"])
+    c = engine.eval_batch(X[:100_000])
+    assert np.array_equal(c["count"], a["count"][:100_000]) and np.array_equal(c["obj"], a["obj"][:100_000])
+    idx = np.random.default_rng(0).choice(B, 2000, replace=False)
+    want = orc.eval_batch(X[idx], N, r_max, pts)
+    assert np.array_equal(a["count"][idx], want["count"]) and np.array_equal(a["obj"][idx], want["obj"])

@@ -1,0 +1,77 @@
+"""CPU-only: host-side logic around the path (data formats, synthetic inputs, list handling)."""
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_fire_rows_roundtrip(cov, fire_rows, tmp_path):
+    p = str(tmp_path / "rows.npz")
+    cov.fire_io.save_fire_rows_npz(p, fire_rows)
+    back = cov.fire_io.load_fire_rows_npz(p)
+    assert len(back) == len(fire_rows) and all(np.array_equal(a, b) for a, b in zip(back, fire_rows))
+
+
+def test_fire_rows_on_lattice(cov, fire_rows):
+    allp = np.concatenate(fire_rows)
+    pl = cov.AreaCoverageCalculation.PointList(allp, 100, 100, 5.0, 5.0)
+    idx = pl.cell_index()
+    i, j = idx % 100 + 1, idx // 100 + 1
+    assert np.array_equal(i * 5.0 - 2.5, allp[:, 0]) and np.array_equal(j * 5.0 - 2.5, allp[:, 1])
+    assert allp[:, 0].min() == 7.5 and allp[:, 0].max() == 492.5 and allp[:, 1].max() == 352.5
+
+
+def test_pack_unpack_bits(cov):
+    rng = np.random.default_rng(1)
+    for nx, ny in ((100, 100), (256, 64), (33, 7), (1, 1), (64, 3)):
+        fire = rng.random((nx, ny)) < 0.4
+        bits = cov.synth.pack_bits(fire)
+        assert bits.shape == (ny, (nx + 31) // 32) and bits.dtype == np.uint32
+        assert np.array_equal(cov.synth.unpack_bits(bits, nx), fire)
+        i, j = nx // 2, ny // 2
+        assert bool((bits[j, i >> 5] >> np.uint32(i & 31)) & np.uint32(1)) == bool(fire[i, j])
+
+
+def test_fire_grid_deterministic(cov):
+    a, na = cov.synth.fire_grid(256)
+    b, nb = cov.synth.fire_grid(256)
+    assert np.array_equal(a, b) and na == nb and 0.15 < na / 256 ** 2 < 0.5
+    d, nd = cov.synth.fire_grid(64, dense=True)
+    assert nd == 64 * 64
+
+
+def test_points_from_bits_matches_createPOI(cov, orc):
+    bits, n = cov.synth.fire_grid(32, dense=True)
+    pts = cov.synth.points_from_bits(bits, 32, 5.0, 5.0)
+    assert np.array_equal(pts, orc.createPOI(5.0, 5.0, 32.0, 32.0))
+    assert np.array_equal(cov.AreaCoverageCalculation.createPOI(5.0, 5.0, 32.0, 32.0).data, pts)
+
+
+def test_pointlist_infer(cov, fire_rows):
+    pl = cov.AreaCoverageCalculation.PointList.infer(np.concatenate(fire_rows[:10]))
+    assert (pl.dx, pl.dy) == (5.0, 5.0) and pl.nx >= 60 and pl.ny >= 69
+
+
+def test_make_circles_roundtrip(cov):
+    x = np.arange(15, dtype=np.float64)
+    c = cov.AreaCoverageCalculation.make_circles(x)
+    assert (c[1].x, c[1].y, c[1].R) == (1.0, 6.0, 11.0)
+    assert np.array_equal(cov.AreaCoverageCalculation.make_MADS(c), x)
+
+
+def test_allocate_even_circles(cov, kat):
+    import math
+    T = math.tan((100 / 180 * math.pi) / 2)
+    x = cov.Base_Functions.allocate_even_circles(15.0, 5, 10 * T, 250.0, 250.0)
+    assert x.tolist() == kat["kat3"]["x"]
+
+
+def test_candidates_shapes(cov):
+    X = cov.synth.random_candidates(100, 5, seed=1)
+    assert X.shape == (100, 15) and X[:, :10].min() >= 0 and X[:, :10].max() < 500
+    T = cov.TAN_HALF_FOV_DEFAULT
+    assert X[:, 10:].min() >= 5 * T and X[:, 10:].max() <= 30 * T
+    P = cov.synth.philox_candidates(64, 3, seed=99, first_index=1 << 33)
+    assert P.shape == (64, 9) and len(np.unique(P)) == P.size
+    assert np.array_equal(P[10:20], cov.synth.philox_candidates(10, 3, seed=99, first_index=(1 << 33) + 10))

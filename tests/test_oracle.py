@@ -1,0 +1,97 @@
+"""CPU-only: the oracle (C and NumPy restatements) against the golden vectors and each other."""
+import math
+
+import numpy as np
+
+T = math.tan((100 / 180 * math.pi) / 2)
+
+
+def test_kat1_createPOI(orc, npo, kat):
+    pts = orc.createPOI(5.0, 5.0, 100.0, 100.0)
+    assert len(pts) == kat["kat1"]["P"]
+    assert pts[0].tolist() == kat["kat1"]["first"]
+    assert pts[1].tolist() == kat["kat1"]["second"]  # j is the inner loop
+    assert pts[-1].tolist() == kat["kat1"]["last"]
+    assert np.array_equal(pts, npo.createPOI(5.0, 5.0, 100.0, 100.0))
+
+
+def test_kat2_single_discs(orc, npo, kat):
+    pts = orc.createPOI(5.0, 5.0, 100.0, 100.0)
+    for k in kat["kat2"]:
+        area, count, tests = orc.calculateArea(k["disc"], pts)
+        assert (count, area) == (k["count"], k["area"])
+        assert npo.calculateArea(np.array(k["disc"]), pts) == (k["area"], k["count"])
+
+
+def test_tie_is_not_covered(orc):
+    # cell (2.5, 2.5) is at distance exactly 5 from (5.5, 6.5): strict < must reject it
+    pts = np.array([[2.5, 2.5, 25.0, 25.0, 0.0]])
+    assert orc.calculateArea([5.5, 6.5, 5.0], pts)[1] == 0
+    assert orc.calculateArea([5.5, 6.5, math.nextafter(5.0, 6.0)], pts)[1] == 1
+
+
+def test_kat3_kat4_objective(orc, npo, kat):
+    pts = orc.createPOI(5.0, 5.0, 100.0, 100.0)
+    x3 = orc.allocate_even_circles(15.0, 5, 10 * T, 250.0, 250.0)
+    assert x3.tolist() == kat["kat3"]["x"]
+    for name in ("kat3", "kat4"):
+        k = kat[name]
+        obj, count = orc.objective(k["x"], k["r_max"], pts)
+        assert (obj, count) == (k["objective"], k["count"])
+        assert npo.objective(np.array(k["x"]), pts, 5, np.array(k["r_max"])) == (k["objective"], k["count"])
+    assert orc.calculateArea(kat["kat3"]["x"], pts)[2] == 49846  # predicate evaluations incl. early break
+
+
+def test_kat5_fire_list(orc, fire_rows, kat):
+    k = kat["kat5"]
+    allp = np.concatenate(fire_rows)
+    assert (len(fire_rows), len(allp)) == (k["rows"], k["entries"])
+    assert len(np.concatenate(fire_rows[:10])) == k["entries_10"]
+    area, count, _ = orc.calculateArea(k["all_covering_disc"], allp)
+    assert count == k["entries"] and area == 25.0 * k["entries"]  # list entries, not unique cells
+    assert len(np.unique(allp[:, :2], axis=0)) == k["unique"]
+
+
+def test_c_vs_numpy_random(orc, npo):
+    rng = np.random.default_rng(7)
+    pts = orc.createPOI(5.0, 5.0, 100.0, 100.0)
+    r_max = np.full(4, 30 * T)
+    for _ in range(25):
+        x = np.concatenate([rng.random(8) * 500, (5 + rng.random(4) * 25) * T])
+        assert orc.objective(x, r_max, pts) == npo.objective(x, pts, 4, r_max)
+        pre = x + rng.normal(0, 4, 12)
+        assert orc.cons3(x, pre, T, np.full(4, 10.0)) == npo.cons3(x, pre, T, np.full(4, 10.0))
+        assert orc.cons7(x, T) == npo.cons7(x, T)
+        assert orc.cons8(x) == npo.cons8(x)
+        assert orc.cons1_progressive(x, r_max) == npo.cons1_progressive(x, r_max)
+        assert np.array_equal(orc.rmvCoveredPOI(x, pts), npo.rmvCoveredPOI(x, pts))
+
+
+def test_batch_matches_scalar_and_threads(orc):
+    rng = np.random.default_rng(11)
+    pts = orc.createPOI(5.0, 5.0, 40.0, 40.0)
+    N, B = 3, 200
+    X = np.concatenate([rng.random((B, 2 * N)) * 200, (5 + rng.random((B, N)) * 25) * T], axis=1)
+    r_max = np.full(N, 30 * T)
+    pre = X[0] + 1.0
+    one = orc.eval_batch(X, N, r_max, pts, pre=pre, d_lim=10.0, tan_half_fov=T, sep_min=15.0, use_cons7=True,
+                         want_prog=True, threads=1)
+    many = orc.eval_batch(X, N, r_max, pts, pre=pre, d_lim=10.0, tan_half_fov=T, sep_min=15.0, use_cons7=True,
+                          want_prog=True, threads=4)
+    for k in one:
+        assert np.array_equal(one[k], many[k])
+    for b in range(0, B, 17):
+        obj, cnt = orc.objective(X[b], r_max, pts)
+        assert (one["obj"][b], one["count"][b]) == (obj, cnt)
+        ok = orc.cons3(X[b], pre, T, np.full(N, 10.0)) and orc.cons8(X[b]) and orc.cons7(X[b], T)
+        assert bool(one["feasible"][b]) == ok
+
+
+def test_threshold_definition(orc, npo):
+    rng = np.random.default_rng(3)
+    for R in [5.0, 36.0, 11.9175359259421, 1.0, 2.0, 0.5, 1e-3, 1e6, 15.0] + list(rng.random(50) * 40):
+        t = orc.threshold_by_search(R)
+        assert t == npo.threshold_by_search(R)
+        assert math.sqrt(t) >= R and math.sqrt(math.nextafter(t, 0.0)) < R
+    assert orc.threshold_by_search(0.0) == 0.0 and orc.threshold_by_search(-1.0) == 0.0
+    assert orc.threshold_by_search(float("nan")) == 0.0 and orc.threshold_by_search(math.inf) == math.inf
