@@ -301,7 +301,7 @@ extern "C" int cov_set_option(cov_handle *h, int option, int64_t value)
     if (!h) return fail(nullptr, COV_ERR_INVALID, "cov_set_option: NULL handle");
     switch (option) {
     case COV_OPT_KERNEL:
-        if (value < COV_KERNEL_AUTO || value > COV_KERNEL_EXACT) return fail(h, COV_ERR_INVALID, "unknown kernel id");
+        if (value < COV_KERNEL_AUTO || value > COV_KERNEL_SPAN_GENERAL) return fail(h, COV_ERR_INVALID, "unknown kernel id");
         h->cfg.kernel = (int)value;
         return COV_OK;
     case COV_OPT_WARPS_PER_CTA:
@@ -539,6 +539,8 @@ extern "C" int cov_set_grid_cells(cov_handle *h, int64_t nx, int64_t ny, double 
     CK(cudaMemcpyAsync(h->mult.p, mult, ncell, cudaMemcpyHostToDevice, h->stream));
     if (cls) CK(cudaMemcpyAsync(h->cls.p, cls, ncell, cudaMemcpyHostToDevice, h->stream));
     else CK(cudaMemsetAsync(h->cls.p, 0, ncell, h->stream));
+    CK(launch_normalize_cls((const unsigned char *)h->mult.p, (unsigned char *)h->cls.p, (long long)ncell, h->stream));
+    h->launches += 1;
     CK(cudaStreamSynchronize(h->stream));
     return rebuild_planes(h, (int)n_classes, class_weight);
 }
@@ -649,7 +651,7 @@ extern "C" int cov_set_points(cov_handle *h, const double *pts5, int64_t P, int6
     OK(alloc_cells(h));
     const size_t ncell = (size_t)nx * ny;
     CK(cudaMemsetAsync(h->mult.p, 0, ncell + 4, h->stream));
-    CK(cudaMemsetAsync(h->cls.p, 0, ncell + 4, h->stream));
+    CK(cudaMemsetAsync(h->cls.p, 0xff, ncell + 4, h->stream));
     OK(upload_points(h, cell, pcls));
     return rebuild_planes(h, n_classes, cw);
 }
@@ -722,7 +724,7 @@ extern "C" int cov_remove_covered(cov_handle *h, const double *xyR, int64_t N, i
     DeviceGuard dg(h->device);
     if (!h->have_grid) return fail(h, COV_ERR_STATE, "cov_remove_covered: no grid set");
     OK(upload_discs_T(h, xyR, N));
-    CK(launch_remove_covered((unsigned char *)h->mult.p, h->g, (const double *)h->xyT.p, (int)N,
+    CK(launch_remove_covered((unsigned char *)h->mult.p, (unsigned char *)h->cls.p, h->g, (const double *)h->xyT.p, (int)N,
                              (unsigned long long *)h->removed.p, h->stream));
     h->launches += 1;
     unsigned long long *hr = (unsigned long long *)h->h_small + 16;

@@ -118,8 +118,9 @@ __global__ void bits_to_cells_kernel(const uint32_t *__restrict__ bits, int nx, 
          t += (long long)gridDim.x * blockDim.x) {
         const int i = (int)(t % nx), j = (int)(t / nx);
         const uint32_t w = bits[(size_t)j * wpr + (i >> 5)];
-        mult[t] = (w >> (i & 31)) & 1u;
-        cls[t] = 0;
+        const unsigned bit = (w >> (i & 31)) & 1u;
+        mult[t] = (unsigned char)bit;
+        cls[t] = bit ? 0 : 0xffu;
     }
 }
 cudaError_t launch_bits_to_cells(const uint32_t *bits, int nx, int ny, unsigned char *mult,
@@ -157,7 +158,7 @@ __device__ __forceinline__ bool cell_covered(const GridDesc &g, int i1, int j1, 
     return false;
 }
 
-__global__ void remove_covered_kernel(unsigned char *mult, const __grid_constant__ GridDesc g,
+__global__ void remove_covered_kernel(unsigned char *mult, unsigned char *cls, const __grid_constant__ GridDesc g,
                                       const double *__restrict__ xyT, int N, unsigned long long *removed)
 {
     const long long ncell = (long long)g.nx * g.ny;
@@ -170,13 +171,14 @@ __global__ void remove_covered_kernel(unsigned char *mult, const __grid_constant
             if (cell_covered(g, i1, j1, xyT, N)) {
                 mine += m;
                 mult[t] = 0;
+                cls[t] = 0xffu;
             }
         }
     }
     for (int off = 16; off; off >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, off);
     if ((threadIdx.x & 31) == 0 && mine) atomicAdd(removed, mine);
 }
-cudaError_t launch_remove_covered(unsigned char *mult, const GridDesc &g, const double *xyT, int N,
+cudaError_t launch_remove_covered(unsigned char *mult, unsigned char *cls, const GridDesc &g, const double *xyT, int N,
                                   unsigned long long *removed, cudaStream_t s)
 {
     cudaError_t e = cudaMemsetAsync(removed, 0, sizeof(unsigned long long), s);
@@ -184,7 +186,7 @@ cudaError_t launch_remove_covered(unsigned char *mult, const GridDesc &g, const 
     const long long ncell = (long long)g.nx * g.ny;
     const int block = 256;
     const int grid = (int)std::min<long long>((ncell + block - 1) / block, 148 * 8);
-    remove_covered_kernel<<<max(grid, 1), block, 0, s>>>(mult, g, xyT, N, removed);
+    remove_covered_kernel<<<max(grid, 1), block, 0, s>>>(mult, cls, g, xyT, N, removed);
     return cudaGetLastError();
 }
 
@@ -208,29 +210,61 @@ cudaError_t launch_covered_mask(unsigned char *mask, const GridDesc &g, const do
     return cudaGetLastError();
 }
 
-// append list entries: multiplicities add up (saturation reported through *overflow)
+// append list entries: multiplicities add up (saturation / mixed weights reported through *overflow).
+// An empty cell carries class kNoClass; the first entry to arrive claims the cell's class with a
+// byte-wide compare-and-swap, so concurrent entries on one cell cannot misread each other.
+constexpr unsigned kNoClass = 0xffu;
+__device__ __forceinline__ unsigned byte_cas(unsigned char *base, long long idx, unsigned expect, unsigned desired)
+{
+    unsigned int *word = reinterpret_cast<unsigned int *>(base + (idx & ~3ll));
+    const int sh = (int)(idx & 3) * 8;
+    unsigned int old = *word, assumed;
+    do {
+        assumed = old;
+        const unsigned cur = (assumed >> sh) & 0xffu;
+        if (cur != expect) return cur;
+        old = atomicCAS(word, assumed, (assumed & ~(0xffu << sh)) | (desired << sh));
+    } while (old != assumed);
+    return expect;
+}
 __global__ void add_points_kernel(unsigned char *mult, unsigned char *cls, const int *__restrict__ cell_idx,
                                   const unsigned char *__restrict__ cell_cls, long long P, int *overflow)
 {
-    // several entries may hit one cell: serialise per cell with a word-wide atomic on the byte's word
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < P;
          t += (long long)gridDim.x * blockDim.x) {
         const int cell = cell_idx[t];
+        const unsigned k = cell_cls[t];
+        const unsigned seen = byte_cas(cls, cell, kNoClass, k);
+        if (seen != kNoClass && seen != k) {
+            atomicExch(overflow, 2); // entries of different weights on one cell
+            continue;
+        }
         unsigned int *word = reinterpret_cast<unsigned int *>(mult + (cell & ~3));
         const int sh = (cell & 3) * 8;
         unsigned int old = *word, assumed;
         do {
             assumed = old;
-            const unsigned m = (assumed >> sh) & 0xffu;
-            if (m >= 255u) {
+            if (((assumed >> sh) & 0xffu) >= 255u) {
                 atomicExch(overflow, 1);
                 break;
             }
-            if (m != 0 && cls[cell] != cell_cls[t]) atomicExch(overflow, 2); // mixed weights on one cell
             old = atomicCAS(word, assumed, assumed + (1u << sh));
         } while (old != assumed);
-        cls[cell] = cell_cls[t];
     }
+}
+// cells without entries carry kNoClass (after uploads and removals)
+__global__ void normalize_cls_kernel(const unsigned char *__restrict__ mult, unsigned char *cls, long long ncell)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < ncell;
+         t += (long long)gridDim.x * blockDim.x)
+        if (mult[t] == 0) cls[t] = (unsigned char)kNoClass;
+}
+cudaError_t launch_normalize_cls(const unsigned char *mult, unsigned char *cls, long long ncell, cudaStream_t s)
+{
+    const int block = 256;
+    const int grid = (int)std::min<long long>((ncell + block - 1) / block, 148 * 8);
+    normalize_cls_kernel<<<max(grid, 1), block, 0, s>>>(mult, cls, ncell);
+    return cudaGetLastError();
 }
 cudaError_t launch_add_points(unsigned char *mult, unsigned char *cls, const int *cell_idx,
                               const unsigned char *cell_cls, long long P, int *overflow, cudaStream_t s)

@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <cstdint>
 #include "cov_device.cuh"
+#include "cov_kernel_common.cuh"
 #include "cov_kernels.cuh"
 #include "../../include/coverage_cuda.h"
 
@@ -42,17 +43,6 @@ struct __align__(16) DiscParam {
     uint32_t rows;   // r0 | r1 << 16: rows that can hold covered cells (1-based); r0 > r1: none
 };
 static_assert(sizeof(DiscParam) == 32, "DiscParam must be 32 bytes");
-
-__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
-
-__device__ __forceinline__ float int_to_float_small(int i)
-{
-    // exact for 0 <= i < 2^23, one LOP3 + one FADD instead of an I2F conversion
-    return __int_as_float(0x4B000000 | i) - 8388608.0f;
-}
-
-// Julia's max(a, 0.0) for Float64: NaN propagates, max(-0.0, 0.0) = 0.0.
-__device__ __forceinline__ double julia_max0(double v) { return (v != v) ? v : (v > 0.0 ? v : 0.0); }
 
 // Results of the prologue that every lane holds after the call.
 struct CandScalars {
@@ -175,136 +165,11 @@ __device__ __forceinline__ CandScalars candidate_prologue(const GridDesc &g, con
     return r;
 }
 
-// obj = -area + violation*scale, area from exact integer counts (see cov_grid_info.area_exact)
-__device__ __forceinline__ double assemble_objective(const GridDesc &g, const ObjParams &o,
-                                                     const long long *class_cnt, double violation)
-{
-    double area = 0.0;
-    if (g.n_classes == 1) {
-        area = __dmul_rn(g.class_weight[0], (double)class_cnt[0]);
-    } else {
-        for (int k = 0; k < g.n_classes; ++k)
-            area = __dadd_rn(area, __dmul_rn(g.class_weight[k], (double)class_cnt[k]));
-    }
-    return __dadd_rn(-area, __dmul_rn(violation, o.penalty_scale));
-}
-
-// ------------------------------------------------------------------------------------------
-// exact FP64 pieces of the span search
-// ------------------------------------------------------------------------------------------
-struct RowExact {
-    double cx, T, dy2, dx, hdx;
-    int nx;
-    __device__ __forceinline__ double px(int i) const { return cell_centre(i, dx, hdx); }
-    __device__ __forceinline__ bool inside(int i) const
-    {
-        const double ddx = __dsub_rn(px(i), cx);
-        return __dadd_rn(__dmul_rn(ddx, ddx), dy2) < T;
-    }
-};
-
-// Exact [lo, hi] (1-based, inclusive; lo > hi: empty) of the covered columns of one row, walking
-// from the estimates. Correct for ANY estimates: the covered set is contiguous and, if not empty,
-// contains a cell next to the centre, because the FP64 radicand is non-increasing in i while
-// px_i <= cx and non-decreasing while px_i >= cx (every rounding involved is monotone).
-__device__ __noinline__ void exact_span(const RowExact r, int lo_e, int hi_e, int &lo_out, int &hi_out)
-{
-    int i = min(max(lo_e, 1), r.nx);
-    bool found = false;
-    if (r.inside(i)) {
-        found = true;
-    } else if (r.px(i) < r.cx) { // left of the centre: the span, if any, starts to the right
-        for (;;) {
-            ++i;
-            if (i > r.nx) break;
-            if (r.inside(i)) {
-                found = true;
-                break;
-            }
-            if (!(r.px(i) < r.cx)) break; // passed the centre without a hit: empty row
-        }
-    } else { // at or right of the centre
-        for (;;) {
-            --i;
-            if (i < 1) break;
-            if (r.inside(i)) {
-                found = true;
-                break;
-            }
-            if (!(r.px(i) > r.cx)) break;
-        }
-    }
-    if (!found) {
-        lo_out = 1;
-        hi_out = 0;
-        return;
-    }
-    int lo = i;
-    while (lo > 1 && r.inside(lo - 1)) --lo;
-    int h = min(max(hi_e, i), r.nx);
-    if (r.inside(h)) {
-        while (h < r.nx && r.inside(h + 1)) ++h;
-    } else {
-        while (!r.inside(h)) --h; // stops at i at the latest
-    }
-    lo_out = lo;
-    hi_out = h;
-}
-
-// ------------------------------------------------------------------------------------------
-// shared-memory plumbing
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p)
-{
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-// TMA bulk copy global -> shared (1-D, 16-byte granular), completion on an mbarrier
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
-{
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar))
-        : "memory");
-}
-
-template <bool SMEM>
-__device__ __forceinline__ uint32_t ld_plane(const uint32_t *p)
-{
-    return SMEM ? *p : __ldg(p);
-}
-
 struct WarpSmem {
     uint32_t *fb;   // framebuffer band
     double *stage;  // 3N doubles
     DiscParam *dp;  // N records
 };
-
-__host__ __device__ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 struct SmemPlan {
     int planes_bytes;  // 0 when the planes stay in global memory
@@ -321,31 +186,6 @@ __host__ __device__ inline SmemPlan plan_smem(const GridDesc &g, int N, int warp
     p.warp_bytes = p.fb_words * 4 + round_up(3 * N * 8, 16) + N * 32;
     p.total_bytes = p.planes_bytes + warps * p.warp_bytes + 16;
     return p;
-}
-
-__device__ __forceinline__ void stage_planes(const GridDesc &g, uint32_t *planes_s, uint64_t *bar,
-                                             int planes_bytes)
-{
-    // one elected thread issues TMA bulk copies of the (pre-padded) planes; everyone waits
-    if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        mbar_expect_tx(bar, (uint32_t)planes_bytes);
-        const char *src = reinterpret_cast<const char *>(g.planes);
-        char *dst = reinterpret_cast<char *>(planes_s);
-        int left = planes_bytes;
-        while (left > 0) {
-            const int n = left > 65536 ? 65536 : left;
-            bulk_g2s(dst, src, (uint32_t)n, bar);
-            dst += n;
-            src += n;
-            left -= n;
-        }
-    }
-    mbar_wait(bar, 0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -864,7 +704,10 @@ cudaError_t launch_eval(const GridDesc &g, const ObjParams &o, const LaunchCfg &
 #undef COV_LAUNCH_BRUTE
         return cudaGetLastError();
     }
-    // span
+    // small swarms on grids whose framebuffer fits a warp's share of shared memory
+    if (cfg.kernel != COV_KERNEL_SPAN_GENERAL && span_small_applies(g, N, cfg, nullptr, nullptr))
+        return launch_span_small(g, o, cfg, dX, B, out, counter, stream, info);
+    // general span kernel
     const bool multi = !(g.n_planes == 1 && g.n_classes == 1 && g.plane_mult[0] == 1);
     int warps = cfg.warps_per_cta > 0 ? cfg.warps_per_cta : 8;
     const int ctas_per_sm = cfg.ctas_per_sm > 0 ? cfg.ctas_per_sm : 1;

@@ -26,6 +26,12 @@ cudaError_t launch_eval(const GridDesc &g, const ObjParams &o, const LaunchCfg &
                         long long B, const EvalOut &out, unsigned long long *counter,
                         cudaStream_t stream, LaunchInfo *info);
 
+// The small-swarm span kernel (cov_span_small.cu): N <= 8 and a framebuffer that fits shared memory.
+bool span_small_applies(const GridDesc &g, int N, const LaunchCfg &cfg, int *warps_out, int *chunk_out);
+cudaError_t launch_span_small(const GridDesc &g, const ObjParams &o, const LaunchCfg &cfg, const double *dX,
+                              long long B, const EvalOut &out, unsigned long long *counter, cudaStream_t stream,
+                              LaunchInfo *info);
+
 // Would the span kernel keep the planes in shared memory for this grid / N?
 int span_planes_fit_smem(const GridDesc &g, int N, const LaunchCfg &cfg);
 
@@ -39,8 +45,9 @@ cudaError_t launch_fill_full(unsigned char *mult, unsigned char *cls, long long 
 cudaError_t launch_bits_to_cells(const uint32_t *bits, int nx, int ny, unsigned char *mult,
                                  unsigned char *cls, cudaStream_t s);
 // xyT: 3N doubles on the device: cx[N], cy[N], T[N]. removed: one unsigned long long.
-cudaError_t launch_remove_covered(unsigned char *mult, const GridDesc &g, const double *xyT, int N,
+cudaError_t launch_remove_covered(unsigned char *mult, unsigned char *cls, const GridDesc &g, const double *xyT, int N,
                                   unsigned long long *removed, cudaStream_t s);
+cudaError_t launch_normalize_cls(const unsigned char *mult, unsigned char *cls, long long ncell, cudaStream_t s);
 cudaError_t launch_covered_mask(unsigned char *mask, const GridDesc &g, const double *xyT, int N,
                                 cudaStream_t s);
 cudaError_t launch_thresholds(const double *xyR, int N, double *xyT, cudaStream_t s);

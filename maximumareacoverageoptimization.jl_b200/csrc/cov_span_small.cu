@@ -1,0 +1,511 @@
+// cov_span_small.cu -- the small-swarm span kernel of libcoverage_cuda (sm_100a): N <= 8 UAVs and a
+// grid whose union framebuffer fits a warp's share of shared memory (the reference's own
+// configurations: N = 5 on 100 x 100, and BASELINE's 5 x 1M on 256 x 256).
+//
+// Same result as the general span kernel (cov_kernels.cu) -- the count of list entries inside the
+// union of the discs, src/AreaCoverageCalculation.jl:63-110 of /root/reference, plus the objective
+// and constraint outputs -- organised for short candidates:
+//   phase 1  lane k of a warp owns candidate k of a 32- (or 16-) candidate chunk: it reads its
+//            3N doubles, forms the penalty sums and constraint verdicts serially in FP64 (the
+//            reference's own order) and writes one 32-byte record per disc to shared memory.
+//            32 candidates are set up at once instead of one candidate on N of 32 lanes.
+//   phase 2  per candidate, the (disc, row) pairs are FLATTENED over the lanes.  A lane computes
+//            the covered columns [lo, hi] of its row in FP32, in coordinates relative to the
+//            disc's nearest cell (so the FP32 error is ~2^-23 R instead of ~2^-21 * 500 m),
+//            certifies both ends against an error band, and falls back to the exact FP64 walk
+//            only when the band cannot decide.  The interval is OR-ed into the warp's
+//            shared-memory framebuffer with atomicOr; the bits the lane was first to set are
+//            AND-ed with the fire plane words and popcounted: a union count, whatever the order.
+//   phase 3  lane k assembles candidate k's objective; 32 results leave as coalesced stores.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdint>
+#include "cov_device.cuh"
+#include "cov_kernel_common.cuh"
+#include "cov_kernels.cuh"
+#include "../../include/coverage_cuda.h"
+
+namespace cov {
+
+constexpr int kSmallMaxN = 8;
+constexpr int kMaxPasses = 6;   // (disc, row) items a lane can remember for the targeted clear
+
+struct __align__(16) SDisc {
+    float fx, fy;     // centre minus the centre of cell (ic, jc)
+    float Tf, delta;  // s_f < Tf - delta: certainly inside; s_f > Tf + delta: certainly outside
+    float icf, jcf;   // ic, jc (exact integers held as floats)
+    uint32_t rows;    // r0 | r1 << 16, 1-based inclusive; r0 > r1: no rows
+    uint32_t flags;   // bit 0: irregular, every row is decided in FP64
+};
+static_assert(sizeof(SDisc) == 32, "SDisc must be 32 bytes");
+
+__device__ __forceinline__ double cell_centre_any(int i, double d, double half_d)
+{
+    return __dsub_rn(__dmul_rn((double)i, d), half_d);
+}
+
+// One disc of one candidate -> its shared-memory record. Returns the number of rows.
+__device__ __forceinline__ int make_sdisc(const GridDesc &g, double cx, double cy, double R, SDisc &d)
+{
+    const double T = threshold(R);
+    const double big = 1.7976931348623157e308;
+    bool live = (T > 0.0) && (fabs(cx) <= big) && (fabs(cy) <= big);
+    int r0 = 1, r1 = 0;
+    if (live) {
+        if (isinf(R)) {
+            r1 = g.ny;
+        } else {
+            // rows j with |py_j - cy| < R, widened by one row and by the FP64 absorption error of
+            // fl(py - cy) for far-away centres
+            const double extra = (fabs(cy) + R) * 8.8817841970012523e-16 * g.inv_dy; // 2^-50
+            double lo = floor((cy - R) * g.inv_dy + 0.5 - extra);
+            double hi = ceil((cy + R) * g.inv_dy + 0.5 + extra);
+            if (!(lo <= (double)g.ny) || !(hi >= 1.0)) {
+                live = false;
+            } else {
+                r0 = (int)fmax(lo, 1.0);
+                r1 = (int)fmin(hi, (double)g.ny);
+            }
+        }
+    }
+    if (!live) {
+        r0 = 1;
+        r1 = 0;
+    }
+    d.rows = (uint32_t)r0 | ((uint32_t)r1 << 16);
+    // relative frame: nearest cell (ic, jc); everything FP32 sees is a small offset from it
+    const double gx = cx * g.inv_dx + 0.5, gy = cy * g.inv_dy + 0.5;
+    bool regular = live && fabs(gx) < 4194304.0 && fabs(gy) < 4194304.0 && T < 1e30;
+    d.flags = 1u;
+    d.fx = d.fy = d.Tf = d.delta = d.icf = d.jcf = 0.0f;
+    if (regular) {
+        const int ic = __double2int_rn(gx), jc = __double2int_rn(gy);
+        const float fx = (float)__dsub_rn(cx, cell_centre_any(ic, g.dx, g.hdx));
+        const float fy = (float)__dsub_rn(cy, cell_centre_any(jc, g.dy, g.hdy));
+        const float Tf = (float)T;
+        const float rt = sqrtf(Tf);
+        // FP32 error of one relative coordinate (DESIGN.md "error band"):
+        //   2^-23 (|offset| + |f|)  [fma rounding, dxf, f]  +  2^-48 M  [the FP64 roundings of the
+        //   reference's own cell centres and of f], M = max(|cx|, |cy|, extent)
+        const float M = fmaxf(fmaxf(fabsf((float)cx), fabsf((float)cy)), g.extent) * 1.0000002f;
+        const float E = 1.1920929e-07f * (rt + fmaxf(fabsf(fx), fabsf(fy))) + 3.5527137e-15f * M;
+        const float delta = 2.0f * (4.0f * rt * E + 2.0f * E * E + Tf * 4.76837158203125e-07f);
+        if (Tf > 64.0f * E * E && Tf > delta) {
+            d.fx = fx;
+            d.fy = fy;
+            d.Tf = Tf;
+            d.delta = delta;
+            d.icf = (float)ic;
+            d.jcf = (float)jc;
+            d.flags = 0u;
+        }
+    }
+    return r1 - r0 + 1 > 0 ? r1 - r0 + 1 : 0;
+}
+
+struct ItemCtx {
+    const GridDesc *g;
+    const double *xrow;   // the candidate's 3N doubles in global memory (slow path only)
+    int N;
+    int force_exact;
+};
+
+// Exact FP64 span of row j of disc c (the slow path).
+static __device__ __noinline__ void slow_span(const GridDesc &g, const double *xrow, int N, int c, int j, int lo_e,
+                                              int hi_e, int &lo, int &hi)
+{
+    RowExact r;
+    r.cx = xrow[c];
+    const double cy = xrow[N + c];
+    r.T = threshold(xrow[2 * N + c]);
+    r.dx = g.dx;
+    r.hdx = g.hdx;
+    r.nx = g.nx;
+    const double ddy = __dsub_rn(cell_centre(j, g.dy, g.hdy), cy);
+    r.dy2 = __dmul_rn(ddy, ddy);
+    if (!(fabs(r.cx) <= 1.7976931348623157e308) || !(r.T > 0.0)) {
+        lo = 1;
+        hi = 0;
+        return;
+    }
+    exact_span(r, lo_e, hi_e, lo, hi);
+}
+
+// Covered columns [lo, hi] (1-based inclusive, lo > hi: none) of row j for disc d.
+__device__ __forceinline__ void row_span(const ItemCtx &cx, const SDisc &d, int c, int j, int &lo, int &hi)
+{
+    const GridDesc &g = *cx.g;
+    lo = 1;
+    hi = 0;
+    bool slow = (d.flags & 1u) || cx.force_exact;
+    int lo_g = 1, hi_g = g.nx; // guesses handed to the exact walk
+    if (!slow) {
+        const float v = int_to_float_small(j) - d.jcf;
+        const float y = fmaf(v, g.dyf, -d.fy);
+        const float dy2 = y * y;
+        const float thi = d.Tf + d.delta, tlo = d.Tf - d.delta;
+        if (dy2 > thi) return; // the whole row is certainly outside
+        const float w2 = d.Tf - dy2;
+        const float w = sqrtf(fmaxf(w2, 0.0f));
+        float ulo = ceilf((d.fx - w) * g.inv_dxf);
+        float uhi = floorf((d.fx + w) * g.inv_dxf);
+        if (ulo > uhi) {
+            // estimate says "no cell": certain if the two cells around the centre are certainly outside
+            const float ua = floorf(d.fx * g.inv_dxf);
+            const float xa = fmaf(ua, g.dxf, -d.fx), xb = xa + g.dxf;
+            if (fmaf(xa, xa, dy2) > thi && fmaf(xb, xb, dy2) > thi) return;
+            slow = true;
+            ulo = uhi = ua;
+        }
+        const float nxf = int_to_float_small(g.nx);
+        const float lof = fmaxf(d.icf + ulo, 1.0f), hif = fminf(d.icf + uhi, nxf);
+        lo_g = (int)fminf(lof, nxf);
+        hi_g = (int)fmaxf(hif, 1.0f);
+        if (!slow) {
+            if (lof > hif) {
+                slow = true; // the estimated span lies outside the grid: let FP64 confirm
+            } else {
+                const float x_lo = fmaf(lof - d.icf, g.dxf, -d.fx), x_hi = fmaf(hif - d.icf, g.dxf, -d.fx);
+                const float x_lm = x_lo - g.dxf, x_hp = x_hi + g.dxf;
+                const bool ok = (fmaf(x_lo, x_lo, dy2) < tlo) && (fmaf(x_hi, x_hi, dy2) < tlo) &&
+                                (lof == 1.0f || fmaf(x_lm, x_lm, dy2) > thi) &&
+                                (hif == nxf || fmaf(x_hp, x_hp, dy2) > thi);
+                if (ok) {
+                    lo = lo_g;
+                    hi = hi_g;
+                    return;
+                }
+                slow = true;
+            }
+        }
+    } else {
+        const double gx = cx.xrow[c] * g.inv_dx + 0.5;
+        const int gi = (gx >= 1.0) ? ((gx <= (double)g.nx) ? (int)gx : g.nx) : 1;
+        lo_g = hi_g = gi;
+    }
+    slow_span(g, cx.xrow, cx.N, c, j, lo_g, hi_g, lo, hi);
+}
+
+// OR [lo, hi] of row j into the framebuffer; popcount the fire bits this lane was first to cover.
+// Returns the packed (row, first word, last word) record for the targeted clear.
+template <bool MULTI>
+__device__ __forceinline__ uint32_t paint_span(const GridDesc &g, uint32_t *fb, const uint32_t *planes, int j, int lo,
+                                               int hi, uint32_t *cnt)
+{
+    const int a = lo - 1, b = hi - 1;
+    const int wa = a >> 5, wb = b >> 5;
+    uint32_t *frow = fb + (j - 1) * g.stride;
+    const uint32_t *prow = planes + (size_t)(j - 1) * g.stride;
+    for (int w = wa; w <= wb; ++w) {
+        uint32_t m = 0xffffffffu;
+        if (w == wa) m &= 0xffffffffu << (a & 31);
+        if (w == wb) m &= 0xffffffffu >> (31 - (b & 31));
+        const uint32_t old = atomicOr(frow + w, m);
+        const uint32_t nw = m & ~old;
+        if (nw) {
+            if (!MULTI) {
+                cnt[0] += __popc(nw & prow[w]);
+            } else {
+                for (int l = 0; l < g.n_planes; ++l) {
+                    const uint32_t v = __popc(nw & prow[(size_t)l * g.plane_words + w]) * g.plane_mult[l];
+                    const int kcls = g.plane_class[l];
+#pragma unroll
+                    for (int k = 0; k < kMaxClasses; ++k) cnt[k] += (k == kcls) ? v : 0u;
+                }
+            }
+        }
+    }
+    return ((uint32_t)(j - 1) << 16) | ((uint32_t)wa << 8) | (uint32_t)wb;
+}
+
+__host__ __device__ inline int small_warp_bytes(const GridDesc &g, int N, int chunk)
+{
+    const int fb = round_up(g.ny * g.stride * 4, 16);
+    const int dp = chunk * N * 32;
+    const int pre = chunk * 16; // 8 x u16 item prefixes per candidate
+    return fb + dp + pre;
+}
+
+template <bool MULTI, int CHUNK>
+__global__ void __launch_bounds__(512, 1)
+span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjParams o,
+                  const double *__restrict__ X, long long B, EvalOut out, unsigned long long *counter,
+                  int force_exact)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t lane = lane_id();
+    const int N = o.N;
+    const int planes_bytes = g.n_planes * g.plane_words * 4;
+    const int warp_bytes = small_warp_bytes(g, N, CHUNK);
+    const int fb_bytes = round_up(g.ny * g.stride * 4, 16);
+    uint32_t *planes_s = reinterpret_cast<uint32_t *>(smem_raw);
+    unsigned char *wbase = smem_raw + planes_bytes + (size_t)warp * warp_bytes;
+    uint32_t *fb = reinterpret_cast<uint32_t *>(wbase);
+    SDisc *dp = reinterpret_cast<SDisc *>(wbase + fb_bytes);
+    uint4 *prefix = reinterpret_cast<uint4 *>(wbase + fb_bytes + CHUNK * N * 32);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + planes_bytes + (size_t)warps * warp_bytes);
+
+    stage_planes(g, planes_s, bar, planes_bytes); // TMA bulk copy of the fire planes, once per CTA
+    for (int t = lane; t < fb_bytes / 16; t += 32) reinterpret_cast<uint4 *>(fb)[t] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+
+    const long long n_chunks = (B + CHUNK - 1) / CHUNK;
+    const int cstride = 3 * N;
+    ItemCtx ictx;
+    ictx.g = &g;
+    ictx.N = N;
+    ictx.force_exact = force_exact;
+
+    for (;;) {
+        unsigned long long chunk = 0;
+        if (lane == 0) chunk = atomicAdd(counter, 1ull);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if ((long long)chunk >= n_chunks) break;
+        const long long base = (long long)chunk * CHUNK;
+        const int in_chunk = (int)min((long long)CHUNK, B - base);
+
+        // ---------------- phase 1: lane k sets up candidate k ----------------
+        double my_viol = 0.0, my_prog = 0.0;
+        int my_feas = 1;
+        if ((int)lane < in_chunk) {
+            const double *xr = X + (base + lane) * cstride;
+            double px[kSmallMaxN], py[kSmallMaxN], pr[kSmallMaxN]; // compile-time indices only: registers
+#pragma unroll
+            for (int c = 0; c < kSmallMaxN; ++c) {
+                px[c] = py[c] = pr[c] = 0.0;
+                if (c < N) {
+                    px[c] = __ldg(xr + c);
+                    py[c] = __ldg(xr + N + c);
+                    pr[c] = __ldg(xr + 2 * N + c);
+                }
+            }
+            // penalty: sequential FP64 sum in index order (src/TDM_STATIC_opt.jl:89-93)
+#pragma unroll
+            for (int i = 0; i < kSmallMaxN; ++i)
+                if (i < N) {
+                    const double diff = __dsub_rn(pr[i], o.r_max[i]);
+                    my_viol = __dadd_rn(my_viol, fabs(diff));
+                    if (out.progressive) my_prog = __dadd_rn(my_prog, julia_max0(diff));
+                }
+            bool bad = false;
+            if (o.use_cons3) {
+#pragma unroll
+                for (int i = 0; i < kSmallMaxN; ++i)
+                    if (i < N) {
+                        const double ax = __dsub_rn(o.prev_x[i], px[i]);
+                        const double ay = __dsub_rn(o.prev_y[i], py[i]);
+                        const double az = __dsub_rn(o.prev_z[i], __ddiv_rn(pr[i], o.tan_half_fov));
+                        const double s =
+                            __dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az));
+                        bad |= (s >= o.cons3_G[i]);
+                    }
+            }
+            if (o.use_cons7) {
+#pragma unroll
+                for (int i = 0; i < kSmallMaxN; ++i)
+                    if (i < N) bad |= (py[i] < 200.0) && (pr[i] > o.cons7_R);
+            }
+            if (o.use_cons8) {
+#pragma unroll
+                for (int i = 0; i < kSmallMaxN; ++i)
+#pragma unroll
+                    for (int j2 = i + 1; j2 < kSmallMaxN; ++j2)
+                        if (j2 < N) {
+                            const double ax = __dsub_rn(px[i], px[j2]);
+                            const double ay = __dsub_rn(py[i], py[j2]);
+                            bad |= (__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)) < o.sep_T);
+                        }
+            }
+            my_feas = !bad;
+            uint32_t run = 0;
+            uint32_t pre[kSmallMaxN];
+#pragma unroll
+            for (int c = 0; c < kSmallMaxN; ++c) {
+                pre[c] = 0xffffu;
+                if (c < N) {
+                    SDisc d;
+                    const int rows = make_sdisc(g, px[c], py[c], pr[c], d);
+                    dp[lane * N + c] = d;
+                    run += (uint32_t)rows;
+                    pre[c] = run < 0xfffeu ? run : 0xfffeu; // inclusive prefix, saturated (see phase 2)
+                }
+            }
+            prefix[lane] = make_uint4(pre[0] | (pre[1] << 16), pre[2] | (pre[3] << 16), pre[4] | (pre[5] << 16),
+                                      pre[6] | (pre[7] << 16));
+        }
+        __syncwarp();
+
+        // ---------------- phase 2: one candidate at a time, (disc, row) items over the lanes ----------------
+        long long my_cnt = 0;
+        long long my_cls[kMaxClasses];
+#pragma unroll
+        for (int k = 0; k < kMaxClasses; ++k) my_cls[k] = 0;
+
+        for (int kc = 0; kc < in_chunk; ++kc) {
+            const uint4 pq = prefix[kc];
+            uint32_t pre[kSmallMaxN] = {pq.x & 0xffffu, pq.x >> 16, pq.y & 0xffffu, pq.y >> 16,
+                                        pq.z & 0xffffu, pq.z >> 16, pq.w & 0xffffu, pq.w >> 16};
+            // total number of items = the last real prefix
+            uint32_t total = 0;
+#pragma unroll
+            for (int c = 0; c < kSmallMaxN; ++c)
+                if (c < N) total = pre[c];
+            const SDisc *cdp = dp + kc * N;
+            ictx.xrow = X + (base + kc) * cstride;
+            uint32_t cnt[MULTI ? kMaxClasses : 1];
+#pragma unroll
+            for (int k = 0; k < (MULTI ? kMaxClasses : 1); ++k) cnt[k] = 0;
+
+            auto do_item = [&](uint32_t t) -> uint32_t {
+                // disc index = number of inclusive prefixes <= t
+                int c = 0;
+                uint32_t before = 0u;
+#pragma unroll
+                for (int q = 0; q < kSmallMaxN - 1; ++q)
+                    if (t >= pre[q]) { // prefixes are non-decreasing; unused slots hold 0xffff
+                        c = q + 1;
+                        before = pre[q];
+                    }
+                const SDisc d = cdp[c];
+                const int j = (int)(d.rows & 0xffffu) + (int)(t - before);
+                int lo, hi;
+                row_span(ictx, d, c, j, lo, hi);
+                if (lo > hi) return 0xffffffffu;
+                return paint_span<MULTI>(g, fb, planes_s, j, lo, hi, cnt);
+            };
+
+            if (total >= 0xfffeu) {
+                // a candidate with >= 65534 (disc, row) items cannot happen on a framebuffer that fits
+                // shared memory (ny * 8 < 65534), but stay safe: handled disc by disc
+                for (int c = 0; c < N; ++c) {
+                    const SDisc d = cdp[c];
+                    const int r0 = d.rows & 0xffffu, r1 = d.rows >> 16;
+                    for (int j = r0 + (int)lane; j <= r1; j += 32) {
+                        int lo, hi;
+                        row_span(ictx, d, c, j, lo, hi);
+                        if (lo <= hi) paint_span<MULTI>(g, fb, planes_s, j, lo, hi, cnt);
+                    }
+                }
+                __syncwarp();
+                for (int t = lane; t < fb_bytes / 16; t += 32)
+                    reinterpret_cast<uint4 *>(fb)[t] = make_uint4(0, 0, 0, 0);
+            } else if (total <= 32u * kMaxPasses) {
+                uint32_t rec[kMaxPasses];
+#pragma unroll
+                for (int p = 0; p < kMaxPasses; ++p) {
+                    rec[p] = 0xffffffffu;
+                    const uint32_t t = (uint32_t)p * 32u + lane;
+                    if ((uint32_t)p * 32u < total && t < total) rec[p] = do_item(t);
+                }
+                __syncwarp();
+                // targeted clear: each lane zeroes the words it painted
+#pragma unroll
+                for (int p = 0; p < kMaxPasses; ++p) {
+                    if (rec[p] != 0xffffffffu) {
+                        uint32_t *frow = fb + (rec[p] >> 16) * g.stride;
+                        const int wa = (rec[p] >> 8) & 0xff, wb = rec[p] & 0xff;
+                        for (int w = wa; w <= wb; ++w) frow[w] = 0u;
+                    }
+                }
+            } else {
+                for (uint32_t t = lane; t < total; t += 32) (void)do_item(t);
+                __syncwarp();
+                for (int t = lane; t < fb_bytes / 16; t += 32)
+                    reinterpret_cast<uint4 *>(fb)[t] = make_uint4(0, 0, 0, 0);
+            }
+            __syncwarp();
+
+            long long total_cnt = 0;
+#pragma unroll
+            for (int k = 0; k < (MULTI ? kMaxClasses : 1); ++k) {
+                const long long v = (long long)__reduce_add_sync(0xffffffffu, cnt[k]);
+                total_cnt += v;
+                if ((int)lane == kc) my_cls[k] = v;
+            }
+            if ((int)lane == kc) my_cnt = total_cnt;
+        }
+
+        // ---------------- phase 3: lane k finishes candidate k; coalesced stores ----------------
+        if ((int)lane < in_chunk) {
+            const long long bidx = base + lane;
+            out.obj[bidx] = assemble_objective(g, o, my_cls, my_viol);
+            if (out.count) out.count[bidx] = my_cnt;
+            if (out.feasible) out.feasible[bidx] = (unsigned char)my_feas;
+            if (out.progressive) out.progressive[bidx] = my_prog;
+            if (out.class_count)
+                for (int k = 0; k < g.n_classes; ++k) out.class_count[bidx * g.n_classes + k] = my_cls[k];
+        }
+        __syncwarp(); // dp / prefix are rewritten by the next chunk
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// launcher: returns false when this kernel does not apply (the general span kernel takes over)
+// ------------------------------------------------------------------------------------------
+template <typename K>
+static cudaError_t set_smem_small(K kernel, int bytes)
+{
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+bool span_small_applies(const GridDesc &g, int N, const LaunchCfg &cfg, int *warps_out, int *chunk_out)
+{
+    if (N > kSmallMaxN || g.stride > 255 || g.ny > 65535) return false;
+    const int planes_bytes = g.n_planes * g.plane_words * 4;
+    int best_w = 0, best_chunk = 0;
+    for (int chunk : {32, 16}) {
+        const int per = small_warp_bytes(g, N, chunk);
+        int w = (cfg.max_smem_optin - planes_bytes - 16) / per;
+        w = std::min(w, 16); // __launch_bounds__(512): 16 warps, <= 128 registers per thread
+        if (cfg.warps_per_cta > 0) w = std::min(w, cfg.warps_per_cta);
+        // prefer the 32-candidate chunk unless the 16-candidate one buys >= 25 % more warps
+        if (w >= 4 && (best_w == 0 || w * 4 >= best_w * 5)) {
+            best_w = w;
+            best_chunk = chunk;
+        }
+    }
+    if (best_w < 4) return false;
+    if (warps_out) *warps_out = best_w;
+    if (chunk_out) *chunk_out = best_chunk;
+    return true;
+}
+
+cudaError_t launch_span_small(const GridDesc &g, const ObjParams &o, const LaunchCfg &cfg, const double *dX,
+                              long long B, const EvalOut &out, unsigned long long *counter, cudaStream_t stream,
+                              LaunchInfo *info)
+{
+    int warps = 0, chunk = 0;
+    if (!span_small_applies(g, o.N, cfg, &warps, &chunk)) return cudaErrorInvalidConfiguration;
+    const bool multi = !(g.n_planes == 1 && g.n_classes == 1 && g.plane_mult[0] == 1);
+    const int smem = g.n_planes * g.plane_words * 4 + warps * small_warp_bytes(g, o.N, chunk) + 16;
+    const long long chunks = (B + chunk - 1) / chunk;
+    const int grid = (int)std::min<long long>((chunks + warps - 1) / warps, (long long)cfg.num_sms);
+    if (info) {
+        info->grid = grid;
+        info->block = warps * 32;
+        info->smem_bytes = smem;
+        info->band_rows = g.ny;
+        info->planes_in_smem = 1;
+    }
+    cudaError_t err;
+#define COV_LAUNCH_SMALL(M, C)                                                                             \
+    do {                                                                                                   \
+        err = set_smem_small(span_small_kernel<M, C>, smem);                                               \
+        if (err != cudaSuccess) return err;                                                                \
+        span_small_kernel<M, C><<<grid, warps * 32, smem, stream>>>(g, o, dX, B, out, counter,             \
+                                                                    cfg.force_exact);                      \
+    } while (0)
+    if (multi) {
+        if (chunk == 32) COV_LAUNCH_SMALL(true, 32);
+        else COV_LAUNCH_SMALL(true, 16);
+    } else {
+        if (chunk == 32) COV_LAUNCH_SMALL(false, 32);
+        else COV_LAUNCH_SMALL(false, 16);
+    }
+#undef COV_LAUNCH_SMALL
+    return cudaGetLastError();
+}
+
+} // namespace cov

@@ -9,7 +9,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 T = math.tan((100 / 180 * math.pi) / 2)
-KERNELS = {"span": 1, "brute": 2, "exact": 3}
+KERNELS = {"span": 1, "span_general": 4, "brute": 2, "exact": 3}
 
 
 def rand_candidates(rng, B, N, extent=500.0, hmin=5.0, hmax=30.0):
@@ -178,7 +178,7 @@ def test_near_boundary_adversarial(cov, orc, engine):
             cx = math.nextafter(cx, cx + rng.choice([-1.0, 1.0]))
         rows.append([cx, cy, R])
     X = np.array(rows)
-    for kernel in ("span", "brute"):
+    for kernel in ("span", "span_general", "brute"):
         for fe in (0, 1):
             engine.set_option(cov.OPT_KERNEL, KERNELS[kernel])
             engine.set_option(cov.OPT_FORCE_EXACT, fe)
@@ -198,7 +198,7 @@ def test_non_f32_lattice_and_ragged_width(cov, orc, engine):
     X = np.concatenate([rng.random((800, N)) * 9 - 0.6, rng.random((800, N)) * 15 - 0.8,
                         rng.random((800, N)) * 2.5], axis=1)
     r_max = np.full(N, 1.0)
-    for kernel in ("span", "brute", "exact"):
+    for kernel in ("span", "span_general", "brute", "exact"):
         engine.set_option(cov.OPT_KERNEL, KERNELS[kernel])
         engine.set_params(N, r_max)
         check_against_oracle(cov, orc, engine, X, N, r_max, pts)
@@ -226,7 +226,7 @@ def test_edge_radii_and_far_centres(cov, orc, engine):
         [inf, 250, 250, 250, inf, 10.0],           # inf - inf = NaN in the radicand
         [0, 500, 0, 500, 707.2, 1.0],              # everything within one disc
     ], dtype=np.float64)
-    for kernel in ("span", "brute", "exact"):
+    for kernel in ("span", "span_general", "brute", "exact"):
         engine.set_option(cov.OPT_KERNEL, KERNELS[kernel])
         want = orc.eval_batch(X, N, r_max, pts)
         got = engine.eval_batch(X)
