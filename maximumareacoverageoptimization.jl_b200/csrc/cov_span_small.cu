@@ -28,14 +28,14 @@
 namespace cov {
 
 constexpr int kSmallMaxN = 8;
-constexpr int kMaxPasses = 6;   // (disc, row) items a lane can remember for the targeted clear
 
 struct __align__(16) SDisc {
     float fx, fy;     // centre minus the centre of cell (ic, jc)
     float Tf, delta;  // s_f < Tf - delta: certainly inside; s_f > Tf + delta: certainly outside
     float icf, jcf;   // ic, jc (exact integers held as floats)
     uint32_t rows;    // r0 | r1 << 16, 1-based inclusive; r0 > r1: no rows
-    uint32_t flags;   // bit 0: irregular, every row is decided in FP64
+    uint32_t flags;   // bit 0: irregular, every row is decided in FP64; bit 1: may share cells with
+                      // another disc of the candidate (its rows go through the framebuffer)
 };
 static_assert(sizeof(SDisc) == 32, "SDisc must be 32 bytes");
 
@@ -146,7 +146,7 @@ __device__ __forceinline__ void row_span(const ItemCtx &cx, const SDisc &d, int 
         const float thi = d.Tf + d.delta, tlo = d.Tf - d.delta;
         if (dy2 > thi) return; // the whole row is certainly outside
         const float w2 = d.Tf - dy2;
-        const float w = sqrtf(fmaxf(w2, 0.0f));
+        const float w = w2 > 0.0f ? w2 * rsqrtf(w2) : 0.0f; // an estimate only: the ends are certified below
         float ulo = ceilf((d.fx - w) * g.inv_dxf);
         float uhi = floorf((d.fx + w) * g.inv_dxf);
         if (ulo > uhi) {
@@ -186,36 +186,51 @@ __device__ __forceinline__ void row_span(const ItemCtx &cx, const SDisc &d, int 
     slow_span(g, cx.xrow, cx.N, c, j, lo_g, hi_g, lo, hi);
 }
 
-// OR [lo, hi] of row j into the framebuffer; popcount the fire bits this lane was first to cover.
-// Returns the packed (row, first word, last word) record for the targeted clear.
+// Count the list entries on columns [lo, hi] of row j.  SHARED = false: the disc shares no cell with
+// any other disc of the candidate, so its cells are counted directly.  SHARED = true: the interval
+// is OR-ed into the warp's framebuffer and only the bits this lane was first to set are counted.
 template <bool MULTI>
-__device__ __forceinline__ uint32_t paint_span(const GridDesc &g, uint32_t *fb, const uint32_t *planes, int j, int lo,
-                                               int hi, uint32_t *cnt)
+__device__ __forceinline__ void count_word(const GridDesc &g, const uint32_t *pw, uint32_t nw, uint32_t *cnt)
+{
+    if (!MULTI) {
+        cnt[0] += __popc(nw & pw[0]);
+    } else {
+        for (int l = 0; l < g.n_planes; ++l) {
+            const uint32_t v = __popc(nw & pw[(size_t)l * g.plane_words]) * g.plane_mult[l];
+            const int kcls = g.plane_class[l];
+#pragma unroll
+            for (int k = 0; k < kMaxClasses; ++k) cnt[k] += (k == kcls) ? v : 0u;
+        }
+    }
+}
+
+template <bool MULTI>
+__device__ __forceinline__ void paint_span(const GridDesc &g, uint32_t *fb, const uint32_t *planes, int j, int lo,
+                                           int hi, bool shared, uint32_t *cnt)
 {
     const int a = lo - 1, b = hi - 1;
     const int wa = a >> 5, wb = b >> 5;
-    uint32_t *frow = fb + (j - 1) * g.stride;
-    const uint32_t *prow = planes + (size_t)(j - 1) * g.stride;
-    for (int w = wa; w <= wb; ++w) {
-        uint32_t m = 0xffffffffu;
-        if (w == wa) m &= 0xffffffffu << (a & 31);
-        if (w == wb) m &= 0xffffffffu >> (31 - (b & 31));
-        const uint32_t old = atomicOr(frow + w, m);
-        const uint32_t nw = m & ~old;
-        if (nw) {
-            if (!MULTI) {
-                cnt[0] += __popc(nw & prow[w]);
-            } else {
-                for (int l = 0; l < g.n_planes; ++l) {
-                    const uint32_t v = __popc(nw & prow[(size_t)l * g.plane_words + w]) * g.plane_mult[l];
-                    const int kcls = g.plane_class[l];
-#pragma unroll
-                    for (int k = 0; k < kMaxClasses; ++k) cnt[k] += (k == kcls) ? v : 0u;
-                }
-            }
-        }
+    const int rowoff = (j - 1) * g.stride;
+    uint32_t *frow = fb + rowoff;
+    const uint32_t *prow = planes + rowoff;
+    const uint32_t ma = 0xffffffffu << (a & 31), mb = 0xffffffffu >> (31 - (b & 31));
+    if (wa == wb) {
+        uint32_t m = ma & mb;
+        if (shared) m &= ~atomicOr(frow + wa, m);
+        count_word<MULTI>(g, prow + wa, m, cnt);
+        return;
     }
-    return ((uint32_t)(j - 1) << 16) | ((uint32_t)wa << 8) | (uint32_t)wb;
+    uint32_t m = ma;
+    if (shared) m &= ~atomicOr(frow + wa, m);
+    count_word<MULTI>(g, prow + wa, m, cnt);
+    for (int w = wa + 1; w < wb; ++w) {
+        m = 0xffffffffu;
+        if (shared) m &= ~atomicOr(frow + w, m);
+        count_word<MULTI>(g, prow + w, m, cnt);
+    }
+    m = mb;
+    if (shared) m &= ~atomicOr(frow + wb, m);
+    count_word<MULTI>(g, prow + wb, m, cnt);
 }
 
 __host__ __device__ inline int small_warp_bytes(const GridDesc &g, int N, int chunk)
@@ -319,6 +334,19 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
                         }
             }
             my_feas = !bad;
+            // discs that may share cells with another disc of the candidate (bounding boxes, two cells
+            // of margin; NaN compares false -> "may share")
+            uint32_t shared_mask = 0;
+#pragma unroll
+            for (int a = 0; a < kSmallMaxN; ++a)
+#pragma unroll
+                for (int b2 = a + 1; b2 < kSmallMaxN; ++b2)
+                    if (b2 < N) {
+                        const double sr = pr[a] + pr[b2];
+                        const bool apart = (fabs(px[a] - px[b2]) >= sr + 2.0 * g.dx) ||
+                                           (fabs(py[a] - py[b2]) >= sr + 2.0 * g.dy);
+                        if (!apart) shared_mask |= (1u << a) | (1u << b2);
+                    }
             uint32_t run = 0;
             uint32_t pre[kSmallMaxN];
 #pragma unroll
@@ -327,6 +355,7 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
                 if (c < N) {
                     SDisc d;
                     const int rows = make_sdisc(g, px[c], py[c], pr[c], d);
+                    d.flags |= ((shared_mask >> c) & 1u) << 1;
                     dp[lane * N + c] = d;
                     run += (uint32_t)rows;
                     pre[c] = run < 0xfffeu ? run : 0xfffeu; // inclusive prefix, saturated (see phase 2)
@@ -358,62 +387,66 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
 #pragma unroll
             for (int k = 0; k < (MULTI ? kMaxClasses : 1); ++k) cnt[k] = 0;
 
-            auto do_item = [&](uint32_t t) -> uint32_t {
-                // disc index = number of inclusive prefixes <= t
-                int c = 0;
-                uint32_t before = 0u;
-#pragma unroll
-                for (int q = 0; q < kSmallMaxN - 1; ++q)
-                    if (t >= pre[q]) { // prefixes are non-decreasing; unused slots hold 0xffff
-                        c = q + 1;
-                        before = pre[q];
-                    }
-                const SDisc d = cdp[c];
-                const int j = (int)(d.rows & 0xffffu) + (int)(t - before);
-                int lo, hi;
-                row_span(ictx, d, c, j, lo, hi);
-                if (lo > hi) return 0xffffffffu;
-                return paint_span<MULTI>(g, fb, planes_s, j, lo, hi, cnt);
-            };
-
+            bool any_shared = false;
             if (total >= 0xfffeu) {
-                // a candidate with >= 65534 (disc, row) items cannot happen on a framebuffer that fits
-                // shared memory (ny * 8 < 65534), but stay safe: handled disc by disc
+                // >= 65534 (disc, row) items cannot happen on a framebuffer that fits shared memory, but
+                // stay safe: disc by disc, everything through the framebuffer
                 for (int c = 0; c < N; ++c) {
                     const SDisc d = cdp[c];
                     const int r0 = d.rows & 0xffffu, r1 = d.rows >> 16;
                     for (int j = r0 + (int)lane; j <= r1; j += 32) {
                         int lo, hi;
                         row_span(ictx, d, c, j, lo, hi);
-                        if (lo <= hi) paint_span<MULTI>(g, fb, planes_s, j, lo, hi, cnt);
+                        if (lo <= hi) paint_span<MULTI>(g, fb, planes_s, j, lo, hi, true, cnt);
                     }
                 }
                 __syncwarp();
                 for (int t = lane; t < fb_bytes / 16; t += 32)
                     reinterpret_cast<uint4 *>(fb)[t] = make_uint4(0, 0, 0, 0);
-            } else if (total <= 32u * kMaxPasses) {
-                uint32_t rec[kMaxPasses];
-#pragma unroll
-                for (int p = 0; p < kMaxPasses; ++p) {
-                    rec[p] = 0xffffffffu;
-                    const uint32_t t = (uint32_t)p * 32u + lane;
-                    if ((uint32_t)p * 32u < total && t < total) rec[p] = do_item(t);
-                }
-                __syncwarp();
-                // targeted clear: each lane zeroes the words it painted
-#pragma unroll
-                for (int p = 0; p < kMaxPasses; ++p) {
-                    if (rec[p] != 0xffffffffu) {
-                        uint32_t *frow = fb + (rec[p] >> 16) * g.stride;
-                        const int wa = (rec[p] >> 8) & 0xff, wb = rec[p] & 0xff;
-                        for (int w = wa; w <= wb; ++w) frow[w] = 0u;
-                    }
-                }
             } else {
-                for (uint32_t t = lane; t < total; t += 32) (void)do_item(t);
-                __syncwarp();
-                for (int t = lane; t < fb_bytes / 16; t += 32)
-                    reinterpret_cast<uint4 *>(fb)[t] = make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+                for (uint32_t t = lane; t < total; t += 32) {
+                    // disc index = number of inclusive prefixes <= t (non-decreasing; unused slots 0xffff)
+                    int c = 0;
+                    uint32_t before = 0u;
+#pragma unroll
+                    for (int q = 0; q < kSmallMaxN - 1; ++q)
+                        if (t >= pre[q]) {
+                            c = q + 1;
+                            before = pre[q];
+                        }
+                    const SDisc d = cdp[c];
+                    const int j = (int)(d.rows & 0xffffu) + (int)(t - before);
+                    int lo, hi;
+                    row_span(ictx, d, c, j, lo, hi);
+                    const bool shared = (d.flags & 2u) != 0;
+                    any_shared |= shared;
+                    if (lo <= hi) paint_span<MULTI>(g, fb, planes_s, j, lo, hi, shared, cnt);
+                }
+                // clear what the shared discs painted: every word of their bounding boxes
+                if (__any_sync(0xffffffffu, any_shared)) {
+                    __syncwarp();
+#pragma unroll 1
+                    for (int c = 0; c < N; ++c) {
+                        const SDisc d = cdp[c];
+                        if (!(d.flags & 2u)) continue;
+                        const int r0 = d.rows & 0xffffu, r1 = d.rows >> 16;
+                        int wa = 0, wb = g.wpr - 1;
+                        if (!(d.flags & 1u)) {
+                            // columns within sqrt(Tf + delta) of the centre, one cell of margin
+                            const float hw = ceilf(sqrtf(d.Tf + d.delta) * g.inv_dxf) + 2.0f;
+                            const float nxf = int_to_float_small(g.nx);
+                            const int ca = (int)fminf(fmaxf(d.icf - hw, 1.0f), nxf);
+                            const int cb = (int)fminf(fmaxf(d.icf + hw, 1.0f), nxf);
+                            wa = (ca - 1) >> 5;
+                            wb = (cb - 1) >> 5;
+                        }
+                        for (int j = r0 + (int)lane; j <= r1; j += 32) {
+                            uint32_t *frow = fb + (j - 1) * g.stride;
+                            for (int w = wa; w <= wb; ++w) frow[w] = 0u;
+                        }
+                    }
+                }
             }
             __syncwarp();
 
