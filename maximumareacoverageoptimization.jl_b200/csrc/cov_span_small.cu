@@ -131,63 +131,55 @@ static __device__ __noinline__ void slow_span(const GridDesc &g, const double *x
     exact_span(r, lo_e, hi_e, lo, hi);
 }
 
-// Covered columns [lo, hi] (1-based inclusive, lo > hi: none) of row j for disc d.
-__device__ __forceinline__ void row_span(const ItemCtx &cx, const SDisc &d, int c, int j, int &lo, int &hi)
+// Straight-line FP32 estimate + certification of the covered columns of row j for disc d.
+// Returns kEmpty (certainly no cell), kSpan (certainly exactly [lo, hi]) or kSlow (FP64 decides;
+// lo, hi then hold in-grid guesses for the exact walk).  No branches: two items interleave.
+enum { kEmpty = 0, kSpan = 1, kSlow = 2 };
+__device__ __forceinline__ int fast_span(const GridDesc &g, const SDisc &d, int j, int force_exact, int &lo, int &hi)
 {
-    const GridDesc &g = *cx.g;
-    lo = 1;
-    hi = 0;
-    bool slow = (d.flags & 1u) || cx.force_exact;
-    int lo_g = 1, hi_g = g.nx; // guesses handed to the exact walk
-    if (!slow) {
-        const float v = int_to_float_small(j) - d.jcf;
-        const float y = fmaf(v, g.dyf, -d.fy);
-        const float dy2 = y * y;
-        const float thi = d.Tf + d.delta, tlo = d.Tf - d.delta;
-        if (dy2 > thi) return; // the whole row is certainly outside
-        const float w2 = d.Tf - dy2;
-        const float w = w2 > 0.0f ? w2 * rsqrtf(w2) : 0.0f; // an estimate only: the ends are certified below
-        float ulo = ceilf((d.fx - w) * g.inv_dxf);
-        float uhi = floorf((d.fx + w) * g.inv_dxf);
-        if (ulo > uhi) {
-            // estimate says "no cell": certain if the two cells around the centre are certainly outside
-            const float ua = floorf(d.fx * g.inv_dxf);
-            const float xa = fmaf(ua, g.dxf, -d.fx), xb = xa + g.dxf;
-            if (fmaf(xa, xa, dy2) > thi && fmaf(xb, xb, dy2) > thi) return;
-            slow = true;
-            ulo = uhi = ua;
-        }
-        const float nxf = int_to_float_small(g.nx);
-        const float lof = fmaxf(d.icf + ulo, 1.0f), hif = fminf(d.icf + uhi, nxf);
-        lo_g = (int)fminf(lof, nxf);
-        hi_g = (int)fmaxf(hif, 1.0f);
-        if (!slow) {
-            if (lof > hif) {
-                slow = true; // the estimated span lies outside the grid: let FP64 confirm
-            } else {
-                const float x_lo = fmaf(lof - d.icf, g.dxf, -d.fx), x_hi = fmaf(hif - d.icf, g.dxf, -d.fx);
-                const float x_lm = x_lo - g.dxf, x_hp = x_hi + g.dxf;
-                const bool ok = (fmaf(x_lo, x_lo, dy2) < tlo) && (fmaf(x_hi, x_hi, dy2) < tlo) &&
-                                (lof == 1.0f || fmaf(x_lm, x_lm, dy2) > thi) &&
-                                (hif == nxf || fmaf(x_hp, x_hp, dy2) > thi);
-                if (ok) {
-                    lo = lo_g;
-                    hi = hi_g;
-                    return;
-                }
-                slow = true;
-            }
-        }
-    } else {
-        const double gx = cx.xrow[c] * g.inv_dx + 0.5;
-        const int gi = (gx >= 1.0) ? ((gx <= (double)g.nx) ? (int)gx : g.nx) : 1;
-        lo_g = hi_g = gi;
-    }
-    slow_span(g, cx.xrow, cx.N, c, j, lo_g, hi_g, lo, hi);
+    const float v = int_to_float_small(j) - d.jcf;
+    const float y = fmaf(v, g.dyf, -d.fy);
+    const float dy2 = y * y;
+    const float thi = d.Tf + d.delta, tlo = d.Tf - d.delta;
+    const float w2 = d.Tf - dy2;
+    const float w = w2 > 0.0f ? w2 * rsqrtf(w2) : 0.0f; // an estimate only: the ends are certified below
+    const float ulo = ceilf((d.fx - w) * g.inv_dxf);
+    const float uhi = floorf((d.fx + w) * g.inv_dxf);
+    const bool est_empty = ulo > uhi;
+    // estimate says "no cell": certain if the two cells around the centre are certainly outside
+    const float ua = floorf(d.fx * g.inv_dxf);
+    const float xa = fmaf(ua, g.dxf, -d.fx), xb = xa + g.dxf;
+    const bool ok_empty = (fmaf(xa, xa, dy2) > thi) && (fmaf(xb, xb, dy2) > thi);
+    const float nxf = int_to_float_small(g.nx);
+    const float lof = fmaxf(d.icf + (est_empty ? ua : ulo), 1.0f), hif = fminf(d.icf + (est_empty ? ua : uhi), nxf);
+    const float x_lo = fmaf(lof - d.icf, g.dxf, -d.fx), x_hi = fmaf(hif - d.icf, g.dxf, -d.fx);
+    const float x_lm = x_lo - g.dxf, x_hp = x_hi + g.dxf;
+    const bool ok_span = (fmaf(x_lo, x_lo, dy2) < tlo) && (fmaf(x_hi, x_hi, dy2) < tlo) &&
+                         (lof == 1.0f || fmaf(x_lm, x_lm, dy2) > thi) && (hif == nxf || fmaf(x_hp, x_hp, dy2) > thi) &&
+                         (lof <= hif);
+    lo = (int)fminf(lof, nxf);
+    hi = (int)fmaxf(hif, 1.0f);
+    const bool irregular = (d.flags & 1u) || force_exact;
+    if (irregular) return kSlow;
+    if (dy2 > thi) return kEmpty; // the whole row is certainly outside
+    if (est_empty) return ok_empty ? kEmpty : kSlow;
+    return ok_span ? kSpan : kSlow;
 }
 
-// Count the list entries on columns [lo, hi] of row j.  SHARED = false: the disc shares no cell with
-// any other disc of the candidate, so its cells are counted directly.  SHARED = true: the interval
+// The slow path of an item: FP64 exact walk from the guesses.
+static __device__ __noinline__ void slow_item(const GridDesc &g, const double *xrow, int N, int c, int j, bool irregular,
+                                              int &lo, int &hi)
+{
+    int lo_g = lo, hi_g = hi;
+    if (irregular) {
+        const double gx = xrow[c] * g.inv_dx + 0.5;
+        lo_g = hi_g = (gx >= 1.0) ? ((gx <= (double)g.nx) ? (int)gx : g.nx) : 1;
+    }
+    slow_span(g, xrow, N, c, j, lo_g, hi_g, lo, hi);
+}
+
+// Count the list entries on columns [lo, hi] of row j.  shared = false: the disc shares no cell with
+// any other disc of the candidate, so its cells are counted directly.  shared = true: the interval
 // is OR-ed into the warp's framebuffer and only the bits this lane was first to set are counted.
 template <bool MULTI>
 __device__ __forceinline__ void count_word(const GridDesc &g, const uint32_t *pw, uint32_t nw, uint32_t *cnt)
@@ -204,33 +196,38 @@ __device__ __forceinline__ void count_word(const GridDesc &g, const uint32_t *pw
     }
 }
 
+// valid = false paints nothing (lets two items share one straight-line instruction stream).
 template <bool MULTI>
 __device__ __forceinline__ void paint_span(const GridDesc &g, uint32_t *fb, const uint32_t *planes, int j, int lo,
-                                           int hi, bool shared, uint32_t *cnt)
+                                           int hi, bool valid, bool shared, uint32_t *cnt)
 {
     const int a = lo - 1, b = hi - 1;
     const int wa = a >> 5, wb = b >> 5;
     const int rowoff = (j - 1) * g.stride;
     uint32_t *frow = fb + rowoff;
     const uint32_t *prow = planes + rowoff;
-    const uint32_t ma = 0xffffffffu << (a & 31), mb = 0xffffffffu >> (31 - (b & 31));
-    if (wa == wb) {
-        uint32_t m = ma & mb;
-        if (shared) m &= ~atomicOr(frow + wa, m);
-        count_word<MULTI>(g, prow + wa, m, cnt);
-        return;
+    const uint32_t ma = valid ? 0xffffffffu << (a & 31) : 0u, mb = 0xffffffffu >> (31 - (b & 31));
+    // the first three words without branches (a span of the bench workload touches at most three)
+    const int w1 = min(wa + 1, wb), w2 = min(wa + 2, wb);
+    uint32_t m0 = (wa == wb) ? (ma & mb) : ma;
+    uint32_t m1 = (wb == wa) ? 0u : ((wb == wa + 1) ? mb : 0xffffffffu);
+    uint32_t m2 = (wb <= wa + 1) ? 0u : ((wb == wa + 2) ? mb : 0xffffffffu);
+    if (!valid) m1 = m2 = 0u;
+    if (shared) {
+        if (m0) m0 &= ~atomicOr(frow + wa, m0);
+        if (m1) m1 &= ~atomicOr(frow + w1, m1);
+        if (m2) m2 &= ~atomicOr(frow + w2, m2);
     }
-    uint32_t m = ma;
-    if (shared) m &= ~atomicOr(frow + wa, m);
-    count_word<MULTI>(g, prow + wa, m, cnt);
-    for (int w = wa + 1; w < wb; ++w) {
-        m = 0xffffffffu;
-        if (shared) m &= ~atomicOr(frow + w, m);
-        count_word<MULTI>(g, prow + w, m, cnt);
+    count_word<MULTI>(g, prow + wa, m0, cnt);
+    count_word<MULTI>(g, prow + w1, m1, cnt);
+    count_word<MULTI>(g, prow + w2, m2, cnt);
+    if (valid && wb > wa + 2) {
+        for (int w = wa + 3; w <= wb; ++w) {
+            uint32_t m = (w == wb) ? mb : 0xffffffffu;
+            if (shared) m &= ~atomicOr(frow + w, m);
+            count_word<MULTI>(g, prow + w, m, cnt);
+        }
     }
-    m = mb;
-    if (shared) m &= ~atomicOr(frow + wb, m);
-    count_word<MULTI>(g, prow + wb, m, cnt);
 }
 
 __host__ __device__ inline int small_warp_bytes(const GridDesc &g, int N, int chunk)
@@ -396,32 +393,63 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
                     const int r0 = d.rows & 0xffffu, r1 = d.rows >> 16;
                     for (int j = r0 + (int)lane; j <= r1; j += 32) {
                         int lo, hi;
-                        row_span(ictx, d, c, j, lo, hi);
-                        if (lo <= hi) paint_span<MULTI>(g, fb, planes_s, j, lo, hi, true, cnt);
+                        int st = fast_span(g, d, j, force_exact, lo, hi);
+                        if (st == kSlow) {
+                            slow_item(g, ictx.xrow, N, c, j, (d.flags & 1u) || force_exact, lo, hi);
+                            if (lo <= hi) st = kSpan;
+                            else { st = kEmpty; lo = hi = 1; }
+                        }
+                        paint_span<MULTI>(g, fb, planes_s, j, lo, hi, st == kSpan, true, cnt);
                     }
                 }
                 __syncwarp();
                 for (int t = lane; t < fb_bytes / 16; t += 32)
                     reinterpret_cast<uint4 *>(fb)[t] = make_uint4(0, 0, 0, 0);
             } else {
+                // two items per lane and iteration: independent instruction streams hide the FP32 latencies
 #pragma unroll 1
-                for (uint32_t t = lane; t < total; t += 32) {
+                for (uint32_t t0 = lane; t0 < total; t0 += 64) {
+                    const uint32_t t1 = t0 + 32;
+                    const bool has1 = t1 < total;
                     // disc index = number of inclusive prefixes <= t (non-decreasing; unused slots 0xffff)
-                    int c = 0;
-                    uint32_t before = 0u;
+                    int c0 = 0, c1 = 0;
+                    uint32_t before0 = 0u, before1 = 0u;
 #pragma unroll
-                    for (int q = 0; q < kSmallMaxN - 1; ++q)
-                        if (t >= pre[q]) {
-                            c = q + 1;
-                            before = pre[q];
+                    for (int q = 0; q < kSmallMaxN - 1; ++q) {
+                        if (t0 >= pre[q]) {
+                            c0 = q + 1;
+                            before0 = pre[q];
                         }
-                    const SDisc d = cdp[c];
-                    const int j = (int)(d.rows & 0xffffu) + (int)(t - before);
-                    int lo, hi;
-                    row_span(ictx, d, c, j, lo, hi);
-                    const bool shared = (d.flags & 2u) != 0;
-                    any_shared |= shared;
-                    if (lo <= hi) paint_span<MULTI>(g, fb, planes_s, j, lo, hi, shared, cnt);
+                        if (t1 >= pre[q]) {
+                            c1 = q + 1;
+                            before1 = pre[q];
+                        }
+                    }
+                    if (!has1) {
+                        c1 = c0;
+                        before1 = before0 + 32; // any valid row of the same disc: the result is discarded
+                    }
+                    const SDisc d0 = cdp[c0], d1 = cdp[c1];
+                    const int j0 = (int)(d0.rows & 0xffffu) + (int)(t0 - before0);
+                    const int j1 = (int)(d1.rows & 0xffffu) + (int)(t1 - before1);
+                    int lo0, hi0, lo1, hi1;
+                    int st0 = fast_span(g, d0, j0, force_exact, lo0, hi0);
+                    int st1 = fast_span(g, d1, j1, force_exact, lo1, hi1);
+                    if (!has1) st1 = kEmpty;
+                    if (st0 == kSlow) {
+                        slow_item(g, ictx.xrow, N, c0, j0, (d0.flags & 1u) || force_exact, lo0, hi0);
+                        if (lo0 <= hi0) st0 = kSpan;
+                        else { st0 = kEmpty; lo0 = hi0 = 1; }
+                    }
+                    if (st1 == kSlow) {
+                        slow_item(g, ictx.xrow, N, c1, j1, (d1.flags & 1u) || force_exact, lo1, hi1);
+                        if (lo1 <= hi1) st1 = kSpan;
+                        else { st1 = kEmpty; lo1 = hi1 = 1; }
+                    }
+                    const bool sh0 = (d0.flags & 2u) != 0, sh1 = (d1.flags & 2u) != 0;
+                    any_shared |= sh0 | (sh1 && has1);
+                    paint_span<MULTI>(g, fb, planes_s, j0, lo0, hi0, st0 == kSpan, sh0, cnt);
+                    paint_span<MULTI>(g, fb, planes_s, j1, lo1, hi1, st1 == kSpan, sh1, cnt);
                 }
                 // clear what the shared discs painted: every word of their bounding boxes
                 if (__any_sync(0xffffffffu, any_shared)) {
