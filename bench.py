@@ -37,6 +37,18 @@ sys.path.insert(0, ROOT)
 N_UAV = 5
 GRID_N = 256
 B_PER_GPU = 1_000_000
+SEP_MIN = 0.0
+# other BASELINE configurations (parity-test cases, not the bench line): selectable for profiling only
+WORKLOADS = {
+    "c2": dict(n=5, grid=256, batch=1_000_000, sep=0.0,
+               name="C2: 5 UAVs x 1M random candidates/step/GPU, 256x256 synthetic fire grid (BASELINE.json configs[1])"),
+    "c3": dict(n=50, grid=1024, batch=65_536, sep=15.0,
+               name="C3 (reduced batch): 50 UAVs x 64K candidates/step/GPU, 1024x1024 fire grid, cons8 separation"),
+    "c4": dict(n=200, grid=4096, batch=8_192, sep=15.0,
+               name="C4 (reduced batch): 200 UAVs x 8K candidates/step/GPU, 4096x4096 fire grid, cons8 separation"),
+    "c1": dict(n=5, grid=100, batch=1_000_000, sep=0.0,
+               name="C1 grid (100x100, dx=5, dense createPOI) with 1M random candidates/step/GPU"),
+}
 N_SETS = 4  # device-resident candidate sets rotated between steps: 4 x 120 MB > 126 MB L2
 METRIC = "coverage_objective_evals_per_sec"
 UNIT = "evals/s"
@@ -114,7 +126,7 @@ class ClockSampler:
 
 def make_workload(cov):
     d = 500.0 / GRID_N
-    bits, n_fire = cov.synth.fire_grid(GRID_N)
+    bits, n_fire = cov.synth.fire_grid(GRID_N, dense=(GRID_N == 100))
     r_max = np.full(N_UAV, 30.0 * cov.TAN_HALF_FOV_DEFAULT)
     return bits, n_fire, d, r_max
 
@@ -126,12 +138,12 @@ def cpu_port_rate(cov, bits, d, r_max, seconds: float, threads: int = 0, seed: i
     nthr = c_oracle.num_threads() if threads <= 0 else threads
     X = cov.synth.random_candidates(max(64, 16 * nthr), N_UAV, seed=seed)
     t = time.perf_counter()
-    c_oracle.eval_batch(X, N_UAV, r_max, pts, threads=threads)
+    c_oracle.eval_batch(X, N_UAV, r_max, pts, sep_min=SEP_MIN, threads=threads)
     rate = len(X) / (time.perf_counter() - t)
     n = int(max(len(X), min(rate * seconds, 4_000_000)))
     X = cov.synth.random_candidates(n, N_UAV, seed=seed + 1)
     t = time.perf_counter()
-    out = c_oracle.eval_batch(X, N_UAV, r_max, pts, threads=threads)
+    out = c_oracle.eval_batch(X, N_UAV, r_max, pts, sep_min=SEP_MIN, threads=threads)
     dt = time.perf_counter() - t
     return n / dt, nthr, n, dt, out, X, pts
 
@@ -149,15 +161,15 @@ def run_reference(args):
     # one step = a bounded sample of the workload: sized for ~2 s of CPU work per step
     probe = cov.synth.random_candidates(max(64, 16 * nthr), N_UAV, seed=99)
     t = time.perf_counter()
-    c_oracle.eval_batch(probe, N_UAV, r_max, pts, threads=0)
+    c_oracle.eval_batch(probe, N_UAV, r_max, pts, sep_min=SEP_MIN, threads=0)
     rate = len(probe) / (time.perf_counter() - t)
     per_step = int(max(256, min(rate * 2.0, B_PER_GPU)))
     X = cov.synth.random_candidates(per_step, N_UAV, seed=1)
     for _ in range(args.warmup):
-        c_oracle.eval_batch(X, N_UAV, r_max, pts, threads=0)
+        c_oracle.eval_batch(X, N_UAV, r_max, pts, sep_min=SEP_MIN, threads=0)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        c_oracle.eval_batch(X, N_UAV, r_max, pts, threads=0)
+        c_oracle.eval_batch(X, N_UAV, r_max, pts, sep_min=SEP_MIN, threads=0)
     dt = time.perf_counter() - t0
     value = per_step * args.steps / dt
     sample = f"{per_step} of the workload's {B_PER_GPU} candidates per step, {args.steps} steps"
@@ -183,10 +195,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kernel", default="auto", choices=["auto", "span", "brute", "exact"])
-    ap.add_argument("--batch", type=int, default=B_PER_GPU)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
+    global N_UAV, GRID_N, B_PER_GPU, WORKLOAD, SEP_MIN
+    wl = WORKLOADS[args.workload]
+    N_UAV, GRID_N, B_PER_GPU, WORKLOAD, SEP_MIN = wl["n"], wl["grid"], wl["batch"], wl["name"], wl["sep"]
+    if args.batch > 0:
+        B_PER_GPU = args.batch
+    args.batch = B_PER_GPU
     if args.impl == "reference":
         return run_reference(args)
 
@@ -210,7 +229,7 @@ def main():
     stream = torch.cuda.Stream(device=local)
     eng.set_stream(stream.cuda_stream)  # torch's events see the kernels on this stream
     eng.set_grid_bits(bits, GRID_N, GRID_N, d, d)
-    eng.set_params(N, r_max)
+    eng.set_params(N, r_max, sep_min=SEP_MIN)
     kid = {"auto": cov.KERNEL_AUTO, "span": cov.KERNEL_SPAN, "brute": cov.KERNEL_BRUTE, "exact": cov.KERNEL_EXACT}[args.kernel]
     eng.set_option(cov.OPT_KERNEL, kid)
 
@@ -296,11 +315,11 @@ def main():
             "config": {"workload": WORKLOAD, "uavs": N, "grid": f"{GRID_N}x{GRID_N}", "fire_entries": n_fire,
                        "candidates_per_step_per_gpu": B, "kernel": args.kernel,
                        "l2": f"device inputs rotate over {N_SETS} x {B * row_bytes / 1e6:.0f} MB candidate sets (> 126 MB L2)",
-                       "penalties": "altitude penalty 1e5*sum|R - r_max|"},
+                       "penalties": "altitude penalty 1e5*sum|R - r_max|" + (f" + cons8 separation {SEP_MIN}" if SEP_MIN > 0 else "")},
             "tests_per_sec": value * tests_per_eval,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": None, "peak_source": f"of {peak_kind}",
-                         "bytes_per_eval": bytes_per_eval, "kernel": "span_kernel", "kernel_ms": kernel_ms,
+                         "bytes_per_eval": bytes_per_eval, "kernel": "span_small_kernel" if N <= 8 else "span_kernel", "kernel_ms": kernel_ms,
                          "note": "the kernel is instruction-issue bound, not HBM bound (DESIGN.md); see issue"},
             "issue": {"algorithmic_tests_per_sec_per_gpu": B * tests_per_eval / (kernel_ms * 1e-3),
                       "lane_instr_peak_per_sec": issue_peak,

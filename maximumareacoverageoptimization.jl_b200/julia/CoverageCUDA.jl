@@ -1,0 +1,108 @@
+# CoverageCUDA.jl -- Julia `ccall` binding of libcoverage_cuda (include/coverage_cuda.h).
+#
+# Drop-in for the reference's objective factory: `CoverageCUDA.createObjective(cells, N, r_max)`
+# returns a closure `AreaMaxObjective(x::Vector{Float64})::Float64` with the value semantics of
+# src/TDM_STATIC_opt.jl:82-100, so `SetObjective(p, obj)` (src/TDM_STATIC_opt.jl:125) and
+# src/FullSimulation.jl:84-97 keep working with only the factory swapped.  A batched entry
+# (`objective_batch`) serves a poll-set-at-a-time MADS driver.
+#
+# NOT EXECUTED in this repository's CI: Julia is not installed in the build container or on the GPU
+# box.  The same C entry points are exercised from Python ctypes in tests/test_gpu_parity.py.
+module CoverageCUDA
+
+const LIB = get(ENV, "LIBCOVERAGE_CUDA", joinpath(@__DIR__, "..", "libcoverage_cuda.so"))
+
+struct CovError <: Exception
+    code::Cint
+    msg::String
+end
+
+mutable struct Handle
+    ptr::Ptr{Cvoid}
+    N::Int
+    function Handle(device::Integer = 0)
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:cov_create, LIB), Cint, (Cint, Ref{Ptr{Cvoid}}), device, out)
+        rc == 0 || throw(CovError(rc, unsafe_string(ccall((:cov_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL))))
+        h = new(out[], 0)
+        finalizer(h -> (h.ptr == C_NULL || ccall((:cov_destroy, LIB), Cvoid, (Ptr{Cvoid},), h.ptr); h.ptr = C_NULL), h)
+        return h
+    end
+end
+
+check(h::Handle, rc::Cint) =
+    rc == 0 || throw(CovError(rc, unsafe_string(ccall((:cov_last_error, LIB), Cstring, (Ptr{Cvoid},), h.ptr))))
+
+"Upload the reference's own point list (`Vector{Vector{Float64}}` of [x, y, area, weight, covered])."
+function set_points!(h::Handle, points::Vector{Vector{Float64}}; nx = 100, ny = 100, dx = 5.0, dy = 5.0)
+    flat = Vector{Float64}(undef, 5 * length(points))
+    @inbounds for (p, pt) in enumerate(points), k in 1:5
+        flat[5 * (p - 1) + k] = pt[k]
+    end
+    GC.@preserve flat check(h, ccall((:cov_set_points, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Float64, Float64),
+        h.ptr, flat, length(points), nx, ny, dx, dy))
+end
+
+"createPOI(dx, dy, nx, ny) built on the device (src/AreaCoverageCalculation.jl:11-21)."
+set_grid_full!(h::Handle, nx, ny, dx, dy) =
+    check(h, ccall((:cov_set_grid_full, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Float64, Float64), h.ptr, nx, ny, dx, dy))
+
+"rmvCoveredPOI on the device-resident store (src/CellFunctions.jl:81-108); returns entries removed."
+function remove_covered!(h::Handle, xyR::Vector{Float64})
+    removed = Ref{Int64}(0)
+    GC.@preserve xyR check(h, ccall((:cov_remove_covered, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Ref{Int64}),
+        h.ptr, xyR, length(xyR) ÷ 3, removed))
+    return removed[]
+end
+
+"Captured variables of createObjective / create_cons3 / cons8 / cons7."
+function set_params!(h::Handle, N::Integer, r_max::Vector{Float64}; penalty = 1e5,
+                     prev::Union{Nothing,Vector{Float64}} = nothing, d_lim::Vector{Float64} = fill(10.0, N),
+                     FOV = 100 / 180 * π, sep_min = 0.0, use_cons7 = false)
+    prevp = prev === nothing ? Ptr{Float64}(C_NULL) : pointer(prev)
+    GC.@preserve r_max prev d_lim check(h, ccall((:cov_set_params, LIB), Cint,
+        (Ptr{Cvoid}, Int64, Ptr{Float64}, Float64, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Int32),
+        h.ptr, N, r_max, penalty, prevp, d_lim, tan(FOV / 2), sep_min, use_cons7 ? 1 : 0))
+    h.N = N
+end
+
+"One candidate: AreaMaxObjective(x) (src/TDM_STATIC_opt.jl:83-98)."
+function eval_one(h::Handle, x::Vector{Float64})
+    obj = Ref{Float64}(0.0)
+    GC.@preserve x check(h, ccall((:cov_eval_one, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Float64}), h.ptr, x, obj))
+    return obj[]
+end
+
+"A whole poll set: X is 3N x B (one candidate [x;y;R] per COLUMN, i.e. candidate-major in memory)."
+function objective_batch(h::Handle, X::Matrix{Float64})
+    B = size(X, 2)
+    obj = Vector{Float64}(undef, B); count = Vector{Int64}(undef, B); feasible = Vector{UInt8}(undef, B)
+    GC.@preserve X obj count feasible check(h, ccall((:cov_eval_batch, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Int64}, Ptr{UInt8}),
+        h.ptr, X, B, obj, count, feasible))
+    return obj, count, feasible
+end
+
+"Poll winner with the extreme barrier: (best objective, 1-based column) or (Inf, 0)."
+function argmin_batch(h::Handle, X::Matrix{Float64}; barrier = true)
+    bo = Ref{Float64}(Inf); bi = Ref{Int64}(-1)
+    GC.@preserve X check(h, ccall((:cov_argmin, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Ref{Float64}, Ref{Int64}), h.ptr, X, size(X, 2), barrier ? 1 : 0, bo, bi))
+    return bo[], bi[] + 1
+end
+
+"""
+    createObjective(cells, N, r_max; handle = Handle())
+
+Same signature and value as the reference's `TDM_STATIC_opt.createObjective` (src/TDM_STATIC_opt.jl:82):
+uploads `cells.points_of_interest` once and returns `AreaMaxObjective(x)`.
+"""
+function createObjective(cells, N, r_max; handle::Handle = Handle(), nx = 100, ny = 100, dx = 5.0, dy = 5.0)
+    set_points!(handle, cells.points_of_interest; nx = nx, ny = ny, dx = dx, dy = dy)
+    set_params!(handle, N, collect(Float64, r_max))
+    AreaMaxObjective(x) = eval_one(handle, x)
+    return AreaMaxObjective
+end
+
+end # module

@@ -552,3 +552,52 @@ def test_full_c2_properties(cov, orc, engine):
     idx = np.random.default_rng(0).choice(B, 2000, replace=False)
     want = orc.eval_batch(X[idx], N, r_max, pts)
     assert np.array_equal(a["count"][idx], want["count"]) and np.array_equal(a["obj"][idx], want["obj"])
+
+
+# ---------------------------------------------------------------- the callers: MADS and the receding horizon
+def test_mads_on_gpu_objective_c1(cov, orc, kat):
+    """Config 1: one MADS solve of FullSimulation.jl's default problem on the GPU objective."""
+    CF, OPT, TC, ACC = cov.CellFunctions, cov.TDM_STATIC_opt, cov.TDM_Constraints, cov.AreaCoverageCalculation
+    cells = CF.initialise_POI(CF.Cells(), "static")
+    N, FOV = 5, 100 / 180 * math.pi
+    r_max = np.full(N, 30.0 * T)
+    x0 = cov.Base_Functions.allocate_even_circles(15.0, N, 10 * T, 250.0, 250.0)
+    cells = CF.rmvCoveredPOI(cells, x0)
+    pts = cells.points_of_interest.data.copy()
+    obj = OPT.createObjective(cells, N, r_max)
+    cons3 = TC.create_cons3(ACC.make_circles(x0), FOV, 10 * np.ones(N))
+    f0 = obj(x0)
+    assert f0 == orc.objective(x0, r_max, pts)[0]
+    res, runtime, st = cov.mads.optimize(x0, obj, [TC.cons1, cons3], [], 100, seed=5, return_stats=True)
+    assert runtime > 0 and st["batches"] >= 2 and st["evaluations"] > 30
+    assert np.all(res == np.rint(res))                       # granularity 1.0
+    assert orc.cons3(res, x0, T, np.full(N, 10.0))           # extreme barrier held
+    f1 = obj(res)
+    assert f1 < f0 and f1 == orc.objective(res, r_max, pts)[0]
+    cells.close()
+
+
+def test_receding_horizon_fire_c5(cov, orc, fire_rows):
+    """Config 5: 20 fire-growth steps, each re-optimised with MADS on the GPU objective; the cell list
+    after every step equals the oracle's replay of the same UAV positions."""
+    CF, FS = cov.CellFunctions, cov.FullSimulation
+    params = FS.SimulationParameters(environment_type="dynamic", N_iter=30, seed=11)
+    cells = CF.initialise_POI(CF.Cells(), "dynamic", fire_rows=fire_rows)
+    N = params.N
+    start = cov.Base_Functions.allocate_even_circles(15.0, N, 10 * T, 250.0, 330.0)
+    r_max = params.h_max * T * np.ones(N)
+    inp, outp, runtimes, objs = FS.run_simulation(cells, start, cov.TDM_Constraints.cons1, [], N, r_max, params,
+                                                  Nt_sim=20)
+    assert len(outp) == 20 and all(r > 0 for r in runtimes)
+    # replay on the oracle: same list evolution, same objective value at every step's result
+    ref = np.concatenate(fire_rows[:10])
+    pre = start
+    for t in range(1, 21):
+        if t != 1:
+            ref = np.concatenate([ref, fire_rows[t + 10 - 1]])
+        ref = orc.rmvCoveredPOI(pre, ref)
+        assert orc.cons3(outp[t - 1], pre, T, np.full(N, 10.0))
+        assert objs[t - 1] == orc.objective(outp[t - 1], r_max, ref)[0]
+        pre = outp[t - 1]
+    assert np.array_equal(cells.points_of_interest.data, ref)
+    cells.close()
