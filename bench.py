@@ -159,11 +159,14 @@ def run_reference(args):
     pts = cov.synth.points_from_bits(bits, GRID_N, d, d)
     nthr = c_oracle.num_threads()
     # one step = a bounded sample of the workload: sized for ~2 s of CPU work per step
-    probe = cov.synth.random_candidates(max(64, 16 * nthr), N_UAV, seed=99)
+    probe = cov.synth.random_candidates(max(256, 64 * nthr), N_UAV, seed=99)
+    c_oracle.eval_batch(probe, N_UAV, r_max, pts, sep_min=SEP_MIN, threads=0)  # thread start-up, page-in
     t = time.perf_counter()
     c_oracle.eval_batch(probe, N_UAV, r_max, pts, sep_min=SEP_MIN, threads=0)
     rate = len(probe) / (time.perf_counter() - t)
-    per_step = int(max(256, min(rate * 2.0, B_PER_GPU)))
+    # bounded: the whole --steps/--warmup run should end within ~2 minutes
+    budget_s = 100.0 / max(args.steps + args.warmup, 1)
+    per_step = int(max(256, min(rate * min(2.0, budget_s), B_PER_GPU)))
     X = cov.synth.random_candidates(per_step, N_UAV, seed=1)
     for _ in range(args.warmup):
         c_oracle.eval_batch(X, N_UAV, r_max, pts, sep_min=SEP_MIN, threads=0)
@@ -191,8 +194,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kernel", default="auto", choices=["auto", "span", "brute", "exact"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
