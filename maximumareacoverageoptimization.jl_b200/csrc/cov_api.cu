@@ -690,7 +690,7 @@ extern "C" int cov_get_grid_info(const cov_handle *h, cov_grid_info *info)
     info->n_planes = h->g.n_planes;
     info->n_classes = h->g.n_classes;
     info->area_exact = h->area_exact;
-    info->planes_in_smem = span_planes_fit_smem(h->g, h->have_params ? h->o.N : 1, h->cfg);
+    info->planes_in_smem = span_small_applies(h->g, h->have_params ? h->o.N : 1, h->cfg, nullptr, nullptr) ? 1 : 0;
     return COV_OK;
 }
 

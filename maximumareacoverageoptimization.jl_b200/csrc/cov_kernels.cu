@@ -10,17 +10,12 @@
 //   cons8  : sqrt((xi-xj)^2+(yi-yj)^2) < sep rejects                    src/TDM_Constraints.jl:157-172
 //   cons1_progressive = sum max(R_i - r_max_i, 0)                       src/TDM_Constraints.jl:182-195
 //
-// The list lives on a lattice, so it is held as bit planes (cov_types.h). Three kernels share one
-// per-candidate prologue (thresholds, penalty, constraints):
-//   span   (default) per (disc, row) the covered columns are ONE interval [lo, hi] (the FP64
-//          radicand is monotone in |px - cx|).  Its two ends are estimated in FP32, certified
-//          with an FP32 error band, and decided in FP64 when the band cannot; the interval is
-//          OR-ed into a per-warp shared-memory framebuffer row and the NEWLY set bits are
-//          AND-ed with the fire words and popcounted, which is exactly the reference's
-//          first-covering-disc-wins union count.
-//   brute  every cell against every disc (north_star's formulation): FP32 test with the same
-//          band, FP64 for band cells, ballot + popc.
-//   exact  every cell against every disc in FP64 only (cross-check for the other two).
+// The list lives on a lattice, so it is held as bit planes (cov_types.h).  This file holds the two
+// cell-sweeping kernels and the launcher; the span kernels (the default) are in
+// cov_span_small.cu / cov_span_cta.cu.
+//   brute  every cell against every disc (north_star's formulation): FP32 test with a certified
+//          error band, FP64 for band cells, ballot + popc.
+//   exact  every cell against every disc in FP64 only (cross-check for the others).
 // One warp owns one candidate at a time; a CTA is a batch of warps sharing the staged planes.
 #include <cuda_runtime.h>
 #include <algorithm>
@@ -164,231 +159,6 @@ __device__ __forceinline__ CandScalars candidate_prologue(const GridDesc &g, con
     r.feasible = !__any_sync(0xffffffffu, bad);
     return r;
 }
-
-struct WarpSmem {
-    uint32_t *fb;   // framebuffer band
-    double *stage;  // 3N doubles
-    DiscParam *dp;  // N records
-};
-
-struct SmemPlan {
-    int planes_bytes;  // 0 when the planes stay in global memory
-    int fb_words;      // per warp
-    int warp_bytes;    // per warp, multiple of 16
-    int total_bytes;
-};
-__host__ __device__ inline SmemPlan plan_smem(const GridDesc &g, int N, int warps, int band_rows,
-                                              bool planes_in_smem, bool want_fb)
-{
-    SmemPlan p;
-    p.planes_bytes = planes_in_smem ? g.n_planes * g.plane_words * 4 : 0;
-    p.fb_words = want_fb ? round_up(band_rows * g.stride, 4) : 0;
-    p.warp_bytes = p.fb_words * 4 + round_up(3 * N * 8, 16) + N * 32;
-    p.total_bytes = p.planes_bytes + warps * p.warp_bytes + 16;
-    return p;
-}
-
-// ------------------------------------------------------------------------------------------
-// span kernel
-// ------------------------------------------------------------------------------------------
-// MULTI = false: one plane, one class, multiplicity 1 (the static grid and synthetic fire grids).
-template <bool MULTI, bool PLANES_SMEM>
-__global__ void __launch_bounds__(512)
-span_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjParams o,
-            const double *__restrict__ X, long long B, EvalOut out, unsigned long long *counter,
-            int band_rows, int force_exact)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warps = blockDim.x >> 5;
-    const int warp = threadIdx.x >> 5;
-    const uint32_t lane = lane_id();
-    const int N = o.N;
-    const SmemPlan plan = plan_smem(g, N, warps, band_rows, PLANES_SMEM, true);
-    uint32_t *planes_s = reinterpret_cast<uint32_t *>(smem_raw);
-    unsigned char *wbase = smem_raw + plan.planes_bytes + (size_t)warp * plan.warp_bytes;
-    uint32_t *fb = reinterpret_cast<uint32_t *>(wbase);
-    double *stage = reinterpret_cast<double *>(wbase + plan.fb_words * 4);
-    DiscParam *dp = reinterpret_cast<DiscParam *>(wbase + plan.fb_words * 4 + round_up(3 * N * 8, 16));
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + plan.planes_bytes + (size_t)warps * plan.warp_bytes);
-
-    if (PLANES_SMEM) stage_planes(g, planes_s, bar, plan.planes_bytes);
-    const uint32_t *planes = PLANES_SMEM ? planes_s : g.planes;
-
-    // clear this warp's framebuffer once; it is cleared again after every band that touched it
-    for (int t = lane; t < plan.fb_words / 4; t += 32) reinterpret_cast<uint4 *>(fb)[t] = make_uint4(0, 0, 0, 0);
-    __syncwarp();
-
-    const int n_bands = (g.ny + band_rows - 1) / band_rows;
-    const long long n_chunks = (B + 31) / 32;
-    const int cstride = 3 * N;
-
-    for (;;) {
-        unsigned long long chunk = 0;
-        if (lane == 0) chunk = atomicAdd(counter, 1ull);
-        chunk = __shfl_sync(0xffffffffu, chunk, 0);
-        if ((long long)chunk >= n_chunks) break;
-        const long long base = (long long)chunk * 32;
-        const int in_chunk = (int)min(32ll, B - base);
-
-        double my_obj = 0.0, my_prog = 0.0;
-        long long my_cnt = 0;
-        long long my_cls[kMaxClasses];
-#pragma unroll
-        for (int k = 0; k < kMaxClasses; ++k) my_cls[k] = 0;
-        int my_feas = 0;
-
-        for (int kc = 0; kc < in_chunk; ++kc) {
-            const double *xc = X + (base + kc) * cstride;
-            for (int t = lane; t < cstride; t += 32) stage[t] = __ldg(xc + t);
-            __syncwarp();
-            const CandScalars cs = candidate_prologue<true>(g, o, stage, dp, out.progressive != nullptr);
-            __syncwarp();
-
-            uint32_t cnt[MULTI ? kMaxClasses : 1];
-#pragma unroll
-            for (int k = 0; k < (MULTI ? kMaxClasses : 1); ++k) cnt[k] = 0;
-
-            for (int band = 0; band < n_bands; ++band) {
-                const int band_lo = band * band_rows + 1;
-                const int band_hi = min(g.ny, band_lo + band_rows - 1);
-                bool touched = false;
-                for (int cb = 0; cb < N; cb += 32) {
-                    const int cme = cb + lane;
-                    bool hit = false;
-                    if (cme < N) {
-                        const uint32_t rows = dp[cme].rows;
-                        const int r0 = rows & 0xffff, r1 = rows >> 16;
-                        hit = (r0 <= r1) && (r0 <= band_hi) && (r1 >= band_lo);
-                    }
-                    uint32_t hits = __ballot_sync(0xffffffffu, hit);
-                    while (hits) {
-                        const int c = cb + __ffs(hits) - 1;
-                        hits &= hits - 1;
-                        touched = true;
-                        const DiscParam d = dp[c];
-                        const int rs = max((int)(d.rows & 0xffff), band_lo);
-                        const int re = min((int)(d.rows >> 16), band_hi);
-                        for (int row0 = rs; row0 <= re; row0 += 32) {
-                            const int j = row0 + lane;
-                            if (j <= re) {
-                                // ---- FP32 estimate of the span ends ----
-                                const float pyf = fmaf(int_to_float_small(j), g.dyf, -g.hdyf);
-                                const float ddy = pyf - d.cyf;
-                                const float dy2 = ddy * ddy;
-                                bool empty = !force_exact && (dy2 > d.thi);
-                                int lo = 1, hi = 0;
-                                if (!empty) {
-                                    const float w = sqrtf(fmaxf(d.Tf - dy2, 0.0f));
-                                    int lo_e = __float2int_rd(fmaf(d.cxf - w, g.inv_dxf, 0.5f)) + 1;
-                                    int hi_e = __float2int_ru(fmaf(d.cxf + w, g.inv_dxf, 0.5f)) - 1;
-                                    lo_e = max(lo_e, 1);
-                                    hi_e = min(hi_e, g.nx);
-                                    bool slow = force_exact || (lo_e > hi_e);
-                                    if (!slow) {
-                                        // certify: lo_e inside, lo_e-1 outside, hi_e inside, hi_e+1 outside
-                                        const float x_lo = fmaf(int_to_float_small(lo_e), g.dxf, -g.hdxf) - d.cxf;
-                                        const float x_hi = fmaf(int_to_float_small(hi_e), g.dxf, -g.hdxf) - d.cxf;
-                                        const float s_lo = fmaf(x_lo, x_lo, dy2);
-                                        const float s_hi = fmaf(x_hi, x_hi, dy2);
-                                        const float x_lm = x_lo - g.dxf, x_hp = x_hi + g.dxf;
-                                        const float s_lm = fmaf(x_lm, x_lm, dy2);
-                                        const float s_hp = fmaf(x_hp, x_hp, dy2);
-                                        const bool ok = (s_lo < d.tlo) && (s_hi < d.tlo) &&
-                                                        (lo_e == 1 || s_lm > d.thi) &&
-                                                        (hi_e == g.nx || s_hp > d.thi);
-                                        slow = !ok;
-                                        lo = lo_e;
-                                        hi = hi_e;
-                                    }
-                                    if (slow) {
-                                        RowExact r;
-                                        r.cx = stage[c];
-                                        r.T = d.T;
-                                        r.dx = g.dx;
-                                        r.hdx = g.hdx;
-                                        r.nx = g.nx;
-                                        const double ddyd = __dsub_rn(cell_centre(j, g.dy, g.hdy), stage[N + c]);
-                                        r.dy2 = __dmul_rn(ddyd, ddyd);
-                                        exact_span(r, lo_e, hi_e, lo, hi);
-                                    }
-                                }
-                                if (lo <= hi) {
-                                    const int a = lo - 1, b = hi - 1;
-                                    const int wa = a >> 5, wb = b >> 5;
-                                    uint32_t *frow = fb + (j - band_lo) * g.stride;
-                                    const uint32_t *prow = planes + (size_t)(j - 1) * g.stride;
-                                    for (int w = wa; w <= wb; ++w) {
-                                        uint32_t m = 0xffffffffu;
-                                        if (w == wa) m &= 0xffffffffu << (a & 31);
-                                        if (w == wb) m &= 0xffffffffu >> (31 - (b & 31));
-                                        const uint32_t old = frow[w];
-                                        const uint32_t nw = m & ~old;
-                                        if (nw) {
-                                            frow[w] = old | m;
-                                            if (!MULTI) {
-                                                cnt[0] += __popc(nw & ld_plane<PLANES_SMEM>(prow + w));
-                                            } else {
-                                                for (int l = 0; l < g.n_planes; ++l) {
-                                                    const uint32_t v =
-                                                        __popc(nw & ld_plane<PLANES_SMEM>(
-                                                                        prow + (size_t)l * g.plane_words + w)) *
-                                                        g.plane_mult[l];
-                                                    const int kcls = g.plane_class[l];
-#pragma unroll
-                                                    for (int k = 0; k < kMaxClasses; ++k)
-                                                        cnt[k] += (k == kcls) ? v : 0u;
-                                                }
-                                            }
-                                        }
-                                    }
-                                }
-                            }
-                        }
-                        __syncwarp(); // rows of the next disc may be other lanes' rows of this one
-                    }
-                }
-                if (touched) {
-                    const int words = (band_hi - band_lo + 1) * g.stride;
-                    for (int t = lane; t < (words + 3) / 4; t += 32)
-                        reinterpret_cast<uint4 *>(fb)[t] = make_uint4(0, 0, 0, 0);
-                    __syncwarp();
-                }
-            }
-
-            long long cls_total[kMaxClasses];
-            long long total = 0;
-#pragma unroll
-            for (int k = 0; k < kMaxClasses; ++k) {
-                cls_total[k] = 0;
-                if (k < (MULTI ? kMaxClasses : 1)) {
-                    cls_total[k] = (long long)__reduce_add_sync(0xffffffffu, cnt[k]);
-                    total += cls_total[k];
-                }
-            }
-            const double objv = assemble_objective(g, o, cls_total, cs.violation);
-            if ((int)lane == kc) {
-                my_obj = objv;
-                my_cnt = total;
-                my_feas = cs.feasible;
-                my_prog = cs.progressive;
-#pragma unroll
-                for (int k = 0; k < kMaxClasses; ++k) my_cls[k] = cls_total[k];
-            }
-            __syncwarp(); // stage/dp are rewritten by the next candidate
-        }
-        // coalesced write of the chunk's 32 results
-        if ((int)lane < in_chunk) {
-            const long long bidx = base + lane;
-            out.obj[bidx] = my_obj;
-            if (out.count) out.count[bidx] = my_cnt;
-            if (out.feasible) out.feasible[bidx] = (unsigned char)my_feas;
-            if (out.progressive) out.progressive[bidx] = my_prog;
-            if (out.class_count)
-                for (int k = 0; k < g.n_classes; ++k) out.class_count[bidx * g.n_classes + k] = my_cls[k];
-        }
-    }
-}
-
 
 // ------------------------------------------------------------------------------------------
 // brute kernel (north_star's formulation): every cell of every word that holds a list entry is
@@ -615,30 +385,6 @@ exact_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjPara
 // ------------------------------------------------------------------------------------------
 // launcher
 // ------------------------------------------------------------------------------------------
-static int pick_band_rows(const GridDesc &g, int N, const LaunchCfg &cfg, int warps, bool planes_smem,
-                          int budget)
-{
-    if (cfg.band_rows > 0) return min(cfg.band_rows, g.ny);
-    // whole grid per warp if it fits, else the largest multiple of 32 rows that does
-    int rows = g.ny;
-    for (;;) {
-        SmemPlan p = plan_smem(g, N, warps, rows, planes_smem, true);
-        if (p.total_bytes <= budget) return rows;
-        if (rows <= 32) return 0;
-        rows = (rows > 64) ? round_up(rows / 2, 32) : 32;
-    }
-}
-
-int span_planes_fit_smem(const GridDesc &g, int N, const LaunchCfg &cfg)
-{
-    const int warps = cfg.warps_per_cta > 0 ? cfg.warps_per_cta : 8;
-    const int planes_bytes = g.n_planes * g.plane_words * 4;
-    // the planes are worth staging only if at least a 32-row band per warp still fits beside them
-    SmemPlan p = plan_smem(g, N, warps, min(32, g.ny), true, true);
-    (void)planes_bytes;
-    return p.total_bytes <= cfg.max_smem_optin;
-}
-
 template <typename K>
 static cudaError_t set_smem(K kernel, int bytes)
 {
@@ -704,52 +450,10 @@ cudaError_t launch_eval(const GridDesc &g, const ObjParams &o, const LaunchCfg &
 #undef COV_LAUNCH_BRUTE
         return cudaGetLastError();
     }
-    // small swarms on grids whose framebuffer fits a warp's share of shared memory
+    // span kernels: the small-swarm variant when it applies, else one CTA per candidate
     if (cfg.kernel != COV_KERNEL_SPAN_GENERAL && span_small_applies(g, N, cfg, nullptr, nullptr))
         return launch_span_small(g, o, cfg, dX, B, out, counter, stream, info);
-    // general span kernel
-    const bool multi = !(g.n_planes == 1 && g.n_classes == 1 && g.plane_mult[0] == 1);
-    int warps = cfg.warps_per_cta > 0 ? cfg.warps_per_cta : 8;
-    const int ctas_per_sm = cfg.ctas_per_sm > 0 ? cfg.ctas_per_sm : 1;
-    const int budget = cfg.max_smem_optin / ctas_per_sm - (ctas_per_sm > 1 ? 1024 : 0);
-    bool planes_smem = false;
-    {
-        SmemPlan p = plan_smem(g, N, warps, min(32, g.ny), true, true);
-        planes_smem = p.total_bytes <= budget;
-    }
-    int band_rows = pick_band_rows(g, N, cfg, warps, planes_smem, budget);
-    while (band_rows == 0 && warps > 1) { // too many warps for this N / stride: shrink the CTA
-        warps /= 2;
-        band_rows = pick_band_rows(g, N, cfg, warps, planes_smem, budget);
-    }
-    if (band_rows == 0) return cudaErrorInvalidConfiguration;
-    SmemPlan p = plan_smem(g, N, warps, band_rows, planes_smem, true);
-    if (p.total_bytes > cfg.max_smem_optin) return cudaErrorInvalidConfiguration;
-    const long long chunks = (B + 31) / 32;
-    const long long want = (chunks + warps - 1) / warps;
-    const int grid = (int)std::min<long long>(want, (long long)cfg.num_sms * ctas_per_sm);
-    li.grid = grid;
-    li.block = warps * 32;
-    li.smem_bytes = p.total_bytes;
-    li.band_rows = band_rows;
-    li.planes_in_smem = planes_smem;
-    if (info) *info = li;
-#define COV_LAUNCH_SPAN(M, S)                                                                      \
-    do {                                                                                           \
-        err = set_smem(span_kernel<M, S>, p.total_bytes);                                          \
-        if (err != cudaSuccess) return err;                                                        \
-        span_kernel<M, S><<<grid, warps * 32, p.total_bytes, stream>>>(g, o, dX, B, out, counter,  \
-                                                                       band_rows, cfg.force_exact); \
-    } while (0)
-    if (multi) {
-        if (planes_smem) COV_LAUNCH_SPAN(true, true);
-        else COV_LAUNCH_SPAN(true, false);
-    } else {
-        if (planes_smem) COV_LAUNCH_SPAN(false, true);
-        else COV_LAUNCH_SPAN(false, false);
-    }
-#undef COV_LAUNCH_SPAN
-    return cudaGetLastError();
+    return launch_span_cta(g, o, cfg, dX, B, out, counter, stream, info);
 }
 
 } // namespace cov

@@ -32,8 +32,10 @@ cudaError_t launch_span_small(const GridDesc &g, const ObjParams &o, const Launc
                               long long B, const EvalOut &out, unsigned long long *counter, cudaStream_t stream,
                               LaunchInfo *info);
 
-// Would the span kernel keep the planes in shared memory for this grid / N?
-int span_planes_fit_smem(const GridDesc &g, int N, const LaunchCfg &cfg);
+// The general span kernel (cov_span_cta.cu): one CTA per candidate, banded framebuffer.
+cudaError_t launch_span_cta(const GridDesc &g, const ObjParams &o, const LaunchCfg &cfg, const double *dX,
+                            long long B, const EvalOut &out, unsigned long long *counter, cudaStream_t stream,
+                            LaunchInfo *info);
 
 // ---- cell-store kernels (cov_grid_kernels.cu) ----
 // stats[0] = entries, stats[1] = cells, stats[2 + k] = OR of the multiplicities of class k

@@ -22,213 +22,13 @@
 #include <cstdint>
 #include "cov_device.cuh"
 #include "cov_kernel_common.cuh"
+#include "cov_span_common.cuh"
 #include "cov_kernels.cuh"
 #include "../../include/coverage_cuda.h"
 
 namespace cov {
 
 constexpr int kSmallMaxN = 8;
-
-struct __align__(16) SDisc {
-    float fx, fy;     // centre minus the centre of cell (ic, jc)
-    float Tf, delta;  // s_f < Tf - delta: certainly inside; s_f > Tf + delta: certainly outside
-    float icf, jcf;   // ic, jc (exact integers held as floats)
-    uint32_t rows;    // r0 | r1 << 16, 1-based inclusive; r0 > r1: no rows
-    uint32_t flags;   // bit 0: irregular, every row is decided in FP64; bit 1: may share cells with
-                      // another disc of the candidate (its rows go through the framebuffer)
-};
-static_assert(sizeof(SDisc) == 32, "SDisc must be 32 bytes");
-
-__device__ __forceinline__ double cell_centre_any(int i, double d, double half_d)
-{
-    return __dsub_rn(__dmul_rn((double)i, d), half_d);
-}
-
-// One disc of one candidate -> its shared-memory record. Returns the number of rows.
-__device__ __forceinline__ int make_sdisc(const GridDesc &g, double cx, double cy, double R, SDisc &d)
-{
-    const double T = threshold(R);
-    const double big = 1.7976931348623157e308;
-    bool live = (T > 0.0) && (fabs(cx) <= big) && (fabs(cy) <= big);
-    int r0 = 1, r1 = 0;
-    if (live) {
-        if (isinf(R)) {
-            r1 = g.ny;
-        } else {
-            // rows j with |py_j - cy| < R, widened by one row and by the FP64 absorption error of
-            // fl(py - cy) for far-away centres
-            const double extra = (fabs(cy) + R) * 8.8817841970012523e-16 * g.inv_dy; // 2^-50
-            double lo = floor((cy - R) * g.inv_dy + 0.5 - extra);
-            double hi = ceil((cy + R) * g.inv_dy + 0.5 + extra);
-            if (!(lo <= (double)g.ny) || !(hi >= 1.0)) {
-                live = false;
-            } else {
-                r0 = (int)fmax(lo, 1.0);
-                r1 = (int)fmin(hi, (double)g.ny);
-            }
-        }
-    }
-    if (!live) {
-        r0 = 1;
-        r1 = 0;
-    }
-    d.rows = (uint32_t)r0 | ((uint32_t)r1 << 16);
-    // relative frame: nearest cell (ic, jc); everything FP32 sees is a small offset from it
-    const double gx = cx * g.inv_dx + 0.5, gy = cy * g.inv_dy + 0.5;
-    bool regular = live && fabs(gx) < 4194304.0 && fabs(gy) < 4194304.0 && T < 1e30;
-    d.flags = 1u;
-    d.fx = d.fy = d.Tf = d.delta = d.icf = d.jcf = 0.0f;
-    if (regular) {
-        const int ic = __double2int_rn(gx), jc = __double2int_rn(gy);
-        const float fx = (float)__dsub_rn(cx, cell_centre_any(ic, g.dx, g.hdx));
-        const float fy = (float)__dsub_rn(cy, cell_centre_any(jc, g.dy, g.hdy));
-        const float Tf = (float)T;
-        const float rt = sqrtf(Tf);
-        // FP32 error of one relative coordinate (DESIGN.md "error band"):
-        //   2^-23 (|offset| + |f|)  [fma rounding, dxf, f]  +  2^-48 M  [the FP64 roundings of the
-        //   reference's own cell centres and of f], M = max(|cx|, |cy|, extent)
-        const float M = fmaxf(fmaxf(fabsf((float)cx), fabsf((float)cy)), g.extent) * 1.0000002f;
-        const float E = 1.1920929e-07f * (rt + fmaxf(fabsf(fx), fabsf(fy))) + 3.5527137e-15f * M;
-        const float delta = 2.0f * (4.0f * rt * E + 2.0f * E * E + Tf * 4.76837158203125e-07f);
-        if (Tf > 64.0f * E * E && Tf > delta) {
-            d.fx = fx;
-            d.fy = fy;
-            d.Tf = Tf;
-            d.delta = delta;
-            d.icf = (float)ic;
-            d.jcf = (float)jc;
-            d.flags = 0u;
-        }
-    }
-    return r1 - r0 + 1 > 0 ? r1 - r0 + 1 : 0;
-}
-
-struct ItemCtx {
-    const GridDesc *g;
-    const double *xrow;   // the candidate's 3N doubles in global memory (slow path only)
-    int N;
-    int force_exact;
-};
-
-// Exact FP64 span of row j of disc c (the slow path).
-static __device__ __noinline__ void slow_span(const GridDesc &g, const double *xrow, int N, int c, int j, int lo_e,
-                                              int hi_e, int &lo, int &hi)
-{
-    RowExact r;
-    r.cx = xrow[c];
-    const double cy = xrow[N + c];
-    r.T = threshold(xrow[2 * N + c]);
-    r.dx = g.dx;
-    r.hdx = g.hdx;
-    r.nx = g.nx;
-    const double ddy = __dsub_rn(cell_centre(j, g.dy, g.hdy), cy);
-    r.dy2 = __dmul_rn(ddy, ddy);
-    if (!(fabs(r.cx) <= 1.7976931348623157e308) || !(r.T > 0.0)) {
-        lo = 1;
-        hi = 0;
-        return;
-    }
-    exact_span(r, lo_e, hi_e, lo, hi);
-}
-
-// Straight-line FP32 estimate + certification of the covered columns of row j for disc d.
-// Returns kEmpty (certainly no cell), kSpan (certainly exactly [lo, hi]) or kSlow (FP64 decides;
-// lo, hi then hold in-grid guesses for the exact walk).  No branches: two items interleave.
-enum { kEmpty = 0, kSpan = 1, kSlow = 2 };
-__device__ __forceinline__ int fast_span(const GridDesc &g, const SDisc &d, int j, int force_exact, int &lo, int &hi)
-{
-    const float v = int_to_float_small(j) - d.jcf;
-    const float y = fmaf(v, g.dyf, -d.fy);
-    const float dy2 = y * y;
-    const float thi = d.Tf + d.delta, tlo = d.Tf - d.delta;
-    const float w2 = d.Tf - dy2;
-    const float w = w2 > 0.0f ? w2 * rsqrtf(w2) : 0.0f; // an estimate only: the ends are certified below
-    const float ulo = ceilf((d.fx - w) * g.inv_dxf);
-    const float uhi = floorf((d.fx + w) * g.inv_dxf);
-    const bool est_empty = ulo > uhi;
-    // estimate says "no cell": certain if the two cells around the centre are certainly outside
-    const float ua = floorf(d.fx * g.inv_dxf);
-    const float xa = fmaf(ua, g.dxf, -d.fx), xb = xa + g.dxf;
-    const bool ok_empty = (fmaf(xa, xa, dy2) > thi) && (fmaf(xb, xb, dy2) > thi);
-    const float nxf = int_to_float_small(g.nx);
-    const float lof = fmaxf(d.icf + (est_empty ? ua : ulo), 1.0f), hif = fminf(d.icf + (est_empty ? ua : uhi), nxf);
-    const float x_lo = fmaf(lof - d.icf, g.dxf, -d.fx), x_hi = fmaf(hif - d.icf, g.dxf, -d.fx);
-    const float x_lm = x_lo - g.dxf, x_hp = x_hi + g.dxf;
-    const bool ok_span = (fmaf(x_lo, x_lo, dy2) < tlo) && (fmaf(x_hi, x_hi, dy2) < tlo) &&
-                         (lof == 1.0f || fmaf(x_lm, x_lm, dy2) > thi) && (hif == nxf || fmaf(x_hp, x_hp, dy2) > thi) &&
-                         (lof <= hif);
-    lo = (int)fminf(lof, nxf);
-    hi = (int)fmaxf(hif, 1.0f);
-    const bool irregular = (d.flags & 1u) || force_exact;
-    if (irregular) return kSlow;
-    if (dy2 > thi) return kEmpty; // the whole row is certainly outside
-    if (est_empty) return ok_empty ? kEmpty : kSlow;
-    return ok_span ? kSpan : kSlow;
-}
-
-// The slow path of an item: FP64 exact walk from the guesses.
-static __device__ __noinline__ void slow_item(const GridDesc &g, const double *xrow, int N, int c, int j, bool irregular,
-                                              int &lo, int &hi)
-{
-    int lo_g = lo, hi_g = hi;
-    if (irregular) {
-        const double gx = xrow[c] * g.inv_dx + 0.5;
-        lo_g = hi_g = (gx >= 1.0) ? ((gx <= (double)g.nx) ? (int)gx : g.nx) : 1;
-    }
-    slow_span(g, xrow, N, c, j, lo_g, hi_g, lo, hi);
-}
-
-// Count the list entries on columns [lo, hi] of row j.  shared = false: the disc shares no cell with
-// any other disc of the candidate, so its cells are counted directly.  shared = true: the interval
-// is OR-ed into the warp's framebuffer and only the bits this lane was first to set are counted.
-template <bool MULTI>
-__device__ __forceinline__ void count_word(const GridDesc &g, const uint32_t *pw, uint32_t nw, uint32_t *cnt)
-{
-    if (!MULTI) {
-        cnt[0] += __popc(nw & pw[0]);
-    } else {
-        for (int l = 0; l < g.n_planes; ++l) {
-            const uint32_t v = __popc(nw & pw[(size_t)l * g.plane_words]) * g.plane_mult[l];
-            const int kcls = g.plane_class[l];
-#pragma unroll
-            for (int k = 0; k < kMaxClasses; ++k) cnt[k] += (k == kcls) ? v : 0u;
-        }
-    }
-}
-
-// valid = false paints nothing (lets two items share one straight-line instruction stream).
-template <bool MULTI>
-__device__ __forceinline__ void paint_span(const GridDesc &g, uint32_t *fb, const uint32_t *planes, int j, int lo,
-                                           int hi, bool valid, bool shared, uint32_t *cnt)
-{
-    const int a = lo - 1, b = hi - 1;
-    const int wa = a >> 5, wb = b >> 5;
-    const int rowoff = (j - 1) * g.stride;
-    uint32_t *frow = fb + rowoff;
-    const uint32_t *prow = planes + rowoff;
-    const uint32_t ma = valid ? 0xffffffffu << (a & 31) : 0u, mb = 0xffffffffu >> (31 - (b & 31));
-    // the first three words without branches (a span of the bench workload touches at most three)
-    const int w1 = min(wa + 1, wb), w2 = min(wa + 2, wb);
-    uint32_t m0 = (wa == wb) ? (ma & mb) : ma;
-    uint32_t m1 = (wb == wa) ? 0u : ((wb == wa + 1) ? mb : 0xffffffffu);
-    uint32_t m2 = (wb <= wa + 1) ? 0u : ((wb == wa + 2) ? mb : 0xffffffffu);
-    if (!valid) m1 = m2 = 0u;
-    if (shared) {
-        if (m0) m0 &= ~atomicOr(frow + wa, m0);
-        if (m1) m1 &= ~atomicOr(frow + w1, m1);
-        if (m2) m2 &= ~atomicOr(frow + w2, m2);
-    }
-    count_word<MULTI>(g, prow + wa, m0, cnt);
-    count_word<MULTI>(g, prow + w1, m1, cnt);
-    count_word<MULTI>(g, prow + w2, m2, cnt);
-    if (valid && wb > wa + 2) {
-        for (int w = wa + 3; w <= wb; ++w) {
-            uint32_t m = (w == wb) ? mb : 0xffffffffu;
-            if (shared) m &= ~atomicOr(frow + w, m);
-            count_word<MULTI>(g, prow + w, m, cnt);
-        }
-    }
-}
 
 __host__ __device__ inline int small_warp_bytes(const GridDesc &g, int N, int chunk)
 {
