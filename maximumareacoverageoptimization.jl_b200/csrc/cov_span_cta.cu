@@ -5,16 +5,19 @@
 // src/AreaCoverageCalculation.jl:63-110, src/TDM_STATIC_opt.jl:82-100, src/TDM_Constraints.jl:54-195
 // of /root/reference), organised for candidates that are a lot of work each (50 UAVs on 1024^2:
 // ~4 400 (disc, row) spans; 200 UAVs on 4096^2: ~70 000 spans of ~10 words):
-//   * the CTA's 16 warps share ONE candidate: its 3N doubles are staged in shared memory, the disc
+//   * the CTA's 8 warps share ONE candidate: its 3N doubles are staged in shared memory, the disc
 //     records are built by all threads, the O(N^2) separation test is spread over the warps while one
 //     lane forms the order-dependent penalty sum;
 //   * the union framebuffer lives in shared memory as a BAND of grid rows (the whole grid when it
 //     fits: 1024 x 33 words = 132 KB; 427-row bands for 4096^2);
-//   * per band the (disc, row) items are flattened over all 512 threads (prefix sums of the clipped
-//     row counts in shared memory, warp-uniform binary search + per-lane linear advance), two items
-//     per thread and iteration, atomicOr into the band, popcount of the newly set bits against the
-//     fire planes (read through L1/L2 with ld.global.nc: the planes are shared by every CTA).
-// Persistent grid (one CTA per SM), candidates handed out by an atomic counter.
+//   * per band the work is cut into units of 32 rows of one disc (prefix sums of the unit counts in
+//     shared memory); warps take units in pairs from a shared-memory dispenser, find the disc with a
+//     warp-uniform binary search, and every lane handles one row of each unit: two independent
+//     spans per lane, atomicOr into the band, popcount of the newly set bits against the fire
+//     planes (read through L1/L2 with ld.global.nc: the planes are shared by every CTA).
+// Persistent grid, up to three 256-thread CTAs per SM so that one candidate's serial phases
+// (dispense, stage, setup, barriers) overlap another's span work; candidates come from an atomic
+// counter.
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdint>
@@ -26,31 +29,43 @@
 
 namespace cov {
 
-constexpr int kCtaThreads = 512;
+constexpr int kCtaThreads = 256;
+constexpr int kCtasPerSm = 3;
 
 struct CtaPlan {
-    int stage_bytes, dp_bytes, prefix_bytes, scratch_bytes, fb_bytes, band_rows, total_bytes;
+    int fixed_bytes, fb_bytes, band_rows, total_bytes, ctas_per_sm;
 };
-__host__ __device__ inline CtaPlan cta_plan(const GridDesc &g, int N, int budget, int band_rows_opt)
+__host__ __device__ inline int cta_fixed_bytes(int N)
 {
-    CtaPlan p;
-    p.stage_bytes = round_up(3 * N * 8, 16);
-    p.dp_bytes = N * 32;
-    p.prefix_bytes = round_up((N + 1) * 4, 16);
-    p.scratch_bytes = 1024;
-    const int fixed = p.stage_bytes + p.dp_bytes + p.prefix_bytes + p.scratch_bytes;
+    return round_up(3 * N * 8, 16) + N * 32 + round_up((N + 1) * 4, 16) + 1024;
+}
+static CtaPlan cta_plan(const GridDesc &g, int N, int smem_per_sm, int band_rows_opt, int ctas_opt)
+{
+    CtaPlan p{};
+    p.fixed_bytes = cta_fixed_bytes(N);
     const int row_bytes = g.stride * 4;
-    int rows = (budget - fixed) / row_bytes;
-    if (rows > g.ny) rows = g.ny;
-    if (band_rows_opt > 0 && band_rows_opt < rows) rows = band_rows_opt;
-    p.band_rows = rows;
-    p.fb_bytes = rows > 0 ? round_up(rows * row_bytes, 16) : 0;
-    p.total_bytes = fixed + p.fb_bytes;
+    // as many co-resident CTAs as possible (they overlap each other's serial phases), as long as a
+    // band still holds a useful number of rows
+    int best = 0;
+    for (int ctas = (ctas_opt > 0 ? ctas_opt : kCtasPerSm); ctas >= 1; --ctas) {
+        const int budget = smem_per_sm / ctas - 1024; // 1 KB per CTA is reserved by the system
+        int rows = (budget - p.fixed_bytes) / row_bytes;
+        if (rows > g.ny) rows = g.ny;
+        if (rows >= std::min(g.ny, 96) || ctas == 1) {
+            best = ctas;
+            p.band_rows = rows;
+            break;
+        }
+    }
+    p.ctas_per_sm = best;
+    if (band_rows_opt > 0 && band_rows_opt < p.band_rows) p.band_rows = band_rows_opt;
+    p.fb_bytes = p.band_rows > 0 ? round_up(p.band_rows * row_bytes, 16) : 0;
+    p.total_bytes = p.fixed_bytes + p.fb_bytes;
     return p;
 }
 
 template <bool MULTI>
-__global__ void __launch_bounds__(kCtaThreads, 1)
+__global__ void __launch_bounds__(kCtaThreads, kCtasPerSm)
 span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjParams o,
                 const double *__restrict__ X, long long B, EvalOut out, unsigned long long *counter,
                 int force_exact, int band_rows, int fb_bytes)
@@ -58,7 +73,7 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int nwarps = kCtaThreads / 32;
+    constexpr int nwarps = kCtaThreads / 32;
     const int N = o.N;
     const int cstride = 3 * N;
     double *stage = reinterpret_cast<double *>(smem_raw);
@@ -66,12 +81,14 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
     uint32_t *prefix = reinterpret_cast<uint32_t *>(smem_raw + round_up(3 * N * 8, 16) + N * 32);
     unsigned char *scratch = smem_raw + round_up(3 * N * 8, 16) + N * 32 + round_up((N + 1) * 4, 16);
     uint32_t *fb = reinterpret_cast<uint32_t *>(scratch + 1024);
-    // scratch: [0,8) next candidate; [8,16) violation; [16,24) progressive; [64, 64+16*4*4) per-warp counts
+    // scratch: [0,8) next candidate; [8,16) violation; [16,24) progressive; [24,28) units of the band;
+    //          [28,32) unit dispenser; [512, 512 + nwarps*4*8) per-warp counts
     unsigned long long *s_next = reinterpret_cast<unsigned long long *>(scratch);
     double *s_viol = reinterpret_cast<double *>(scratch + 8);
     double *s_prog = reinterpret_cast<double *>(scratch + 16);
-    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(scratch + 64);       // [nwarps][kMaxClasses]
-    uint32_t *s_carry = reinterpret_cast<uint32_t *>(scratch + 64 + 256); // scan carry
+    uint32_t *s_units = reinterpret_cast<uint32_t *>(scratch + 24);
+    uint32_t *s_disp = reinterpret_cast<uint32_t *>(scratch + 28);
+    unsigned long long *s_cnt = reinterpret_cast<unsigned long long *>(scratch + 512);
 
     for (int t = tid; t < fb_bytes / 16; t += kCtaThreads) reinterpret_cast<uint4 *>(fb)[t] = make_uint4(0, 0, 0, 0);
 
@@ -87,27 +104,25 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
         for (int t = tid; t < cstride; t += kCtaThreads) stage[t] = __ldg(xr + t);
         __syncthreads();
 
-        // ---- B. disc records (all threads) ----
+        // ---- B. disc records (threads from the front) and, at the same time, the order-dependent
+        //         penalty sums on the last thread ----
         for (int c = tid; c < N; c += kCtaThreads) {
             SDisc d;
             make_sdisc(g, stage[c], stage[N + c], stage[2 * N + c], d);
             d.flags |= 2u; // large swarms overlap as a rule: every disc goes through the framebuffer
             dp[c] = d;
         }
-
-        // ---- C. penalty (one lane, the reference's order) and constraints (everyone) ----
-        if (tid == 0) {
+        if (tid == kCtaThreads - 1) {
             double viol = 0.0, prog = 0.0;
             for (int i = 0; i < N; ++i) {
                 const double diff = __dsub_rn(stage[2 * N + i], o.r_max[i]);
                 viol = __dadd_rn(viol, fabs(diff));
+                if (out.progressive) prog = __dadd_rn(prog, julia_max0(diff));
             }
-            if (out.progressive)
-                for (int i = 0; i < N; ++i)
-                    prog = __dadd_rn(prog, julia_max0(__dsub_rn(stage[2 * N + i], o.r_max[i])));
             *s_viol = viol;
             *s_prog = prog;
         }
+        // ---- C. constraints (everyone; a conjunction, so order-free) ----
         bool bad = false;
         if (o.use_cons3) {
             for (int i = tid; i < N; i += kCtaThreads) {
@@ -123,7 +138,7 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
         }
         if (o.use_cons8) {
             // unordered pairs decide the reference's ordered-pair loop ((xi-xj)^2 is symmetric)
-            for (int i = warp; i < N - 1; i += nwarps) {
+            for (int i = nwarps - 1 - warp; i < N - 1; i += nwarps) { // back warps first: the front ones build discs
                 const double xi = stage[i], yi = stage[N + i];
                 for (int j2 = i + 1 + lane; j2 < N; j2 += 32) {
                     const double ax = __dsub_rn(xi, stage[j2]);
@@ -132,19 +147,19 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
                 }
             }
         }
-        const int any_bad = __syncthreads_or(bad ? 1 : 0); // also publishes dp[] and s_viol
+        const int any_bad = __syncthreads_or(bad ? 1 : 0); // also publishes dp[] and the penalty sums
 
         uint32_t cnt[MULTI ? kMaxClasses : 1];
 #pragma unroll
         for (int k = 0; k < (MULTI ? kMaxClasses : 1); ++k) cnt[k] = 0;
-        long long cls_total[kMaxClasses];
+        unsigned long long cls_total[MULTI ? kMaxClasses : 1];
 #pragma unroll
-        for (int k = 0; k < kMaxClasses; ++k) cls_total[k] = 0;
+        for (int k = 0; k < (MULTI ? kMaxClasses : 1); ++k) cls_total[k] = 0;
 
         // ---- D. bands of framebuffer rows ----
         for (int jb0 = 1; jb0 <= g.ny; jb0 += band_rows) {
             const int jb1 = min(g.ny, jb0 + band_rows - 1);
-            // rows of every disc clipped to the band -> inclusive prefix sums in prefix[1..N]
+            // work units = 32-row blocks of a disc's rows inside the band; prefix[c] = first unit of disc c
             if (warp == 0) {
                 uint32_t carry = 0;
                 for (int c0 = 0; c0 < N; c0 += 32) {
@@ -153,7 +168,7 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
                     if (c < N) {
                         const uint32_t rows = dp[c].rows;
                         const int r0 = max((int)(rows & 0xffffu), jb0), r1 = min((int)(rows >> 16), jb1);
-                        n = r1 >= r0 ? (uint32_t)(r1 - r0 + 1) : 0u;
+                        n = r1 >= r0 ? (uint32_t)((r1 - r0 + 32) >> 5) : 0u;
                     }
                     uint32_t incl = n;
 #pragma unroll
@@ -166,87 +181,78 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
                 }
                 if (lane == 0) {
                     prefix[0] = 0;
-                    *s_carry = carry;
+                    *s_units = carry;
+                    *s_disp = 0;
                 }
             }
             __syncthreads();
-            const uint32_t total = *s_carry;
-            if (total == 0) { // uniform across the CTA
-                __syncthreads(); // everyone has read s_carry before warp 0 rewrites it
-                continue;
-            }
-
-            // (disc, row) items over all threads, two per thread and iteration
-            for (uint32_t tb = 0; tb < total; tb += 2 * kCtaThreads) {
-                const uint32_t t0 = tb + tid, t1 = t0 + kCtaThreads;
-                const bool has0 = t0 < total, has1 = t1 < total;
-                int c0 = 0, c1 = 0;
-                {
-                    // warp-uniform binary search for the disc of the warp's first item, then a short
-                    // per-lane advance (32 consecutive items span few discs)
-                    const uint32_t w0 = min(tb + (uint32_t)(warp * 32), total - 1);
-                    const uint32_t w1 = min(w0 + kCtaThreads, total - 1);
-                    int lo = 0, hi = N - 1; // largest c with prefix[c] <= w0
+            const uint32_t units = *s_units;
+            if (units != 0) {
+                // warps take units in pairs from the CTA's dispenser: two independent spans per lane
+                for (;;) {
+                    uint32_t u0 = 0;
+                    if (lane == 0) u0 = atomicAdd(s_disp, 2u);
+                    u0 = __shfl_sync(0xffffffffu, u0, 0);
+                    if (u0 >= units) break;
+                    const uint32_t u1 = min(u0 + 1, units - 1);
+                    const bool has1 = u0 + 1 < units;
+                    // disc of a unit: the largest c with prefix[c] <= u (warp-uniform binary search)
+                    int lo = 0, hi = N - 1;
                     while (lo < hi) {
                         const int mid = (lo + hi + 1) >> 1;
-                        if (prefix[mid] <= w0) lo = mid;
+                        if (prefix[mid] <= u0) lo = mid;
                         else hi = mid - 1;
                     }
-                    c0 = lo;
-                    hi = N - 1;
-                    while (lo < hi) {
-                        const int mid = (lo + hi + 1) >> 1;
-                        if (prefix[mid] <= w1) lo = mid;
-                        else hi = mid - 1;
+                    const int c0 = lo;
+                    int c1 = c0;
+                    while (c1 + 1 < N && prefix[c1 + 1] <= u1) ++c1;
+                    const SDisc d0 = dp[c0], d1 = dp[c1];
+                    const int j0 = max((int)(d0.rows & 0xffffu), jb0) + (int)((u0 - prefix[c0]) << 5) + lane;
+                    const int j1 = max((int)(d1.rows & 0xffffu), jb0) + (int)((u1 - prefix[c1]) << 5) + lane;
+                    const bool in0 = j0 <= min((int)(d0.rows >> 16), jb1);
+                    const bool in1 = has1 && j1 <= min((int)(d1.rows >> 16), jb1);
+                    const int jj0 = in0 ? j0 : jb0, jj1 = in1 ? j1 : jb0; // any row of the band: result discarded
+                    int lo0, hi0, lo1, hi1;
+                    int st0 = fast_span(g, d0, jj0, force_exact, lo0, hi0);
+                    int st1 = fast_span(g, d1, jj1, force_exact, lo1, hi1);
+                    if (!in0) st0 = kEmpty;
+                    if (!in1) st1 = kEmpty;
+                    if (st0 == kSlow) {
+                        slow_item(g, xr, N, c0, jj0, (d0.flags & 1u) || force_exact, lo0, hi0);
+                        if (lo0 <= hi0) st0 = kSpan;
+                        else { st0 = kEmpty; lo0 = hi0 = 1; }
                     }
-                    c1 = lo;
-                    const uint32_t q0 = has0 ? t0 : w0, q1 = has1 ? t1 : w1;
-                    while (c0 + 1 < N && prefix[c0 + 1] <= q0) ++c0;
-                    while (c1 + 1 < N && prefix[c1 + 1] <= q1) ++c1;
+                    if (st1 == kSlow) {
+                        slow_item(g, xr, N, c1, jj1, (d1.flags & 1u) || force_exact, lo1, hi1);
+                        if (lo1 <= hi1) st1 = kSpan;
+                        else { st1 = kEmpty; lo1 = hi1 = 1; }
+                    }
+                    paint_span<MULTI, false>(g, fb, g.planes, jj0, lo0, hi0, st0 == kSpan, true, cnt, jb0);
+                    paint_span<MULTI, false>(g, fb, g.planes, jj1, lo1, hi1, st1 == kSpan, true, cnt, jb0);
                 }
-                const SDisc d0 = dp[c0], d1 = dp[c1];
-                const uint32_t q0 = has0 ? t0 : min(tb + (uint32_t)(warp * 32), total - 1);
-                const uint32_t q1 = has1 ? t1 : min(min(tb + (uint32_t)(warp * 32), total - 1) + kCtaThreads, total - 1);
-                const int j0 = max((int)(d0.rows & 0xffffu), jb0) + (int)(q0 - prefix[c0]);
-                const int j1 = max((int)(d1.rows & 0xffffu), jb0) + (int)(q1 - prefix[c1]);
-                int lo0, hi0, lo1, hi1;
-                int st0 = fast_span(g, d0, j0, force_exact, lo0, hi0);
-                int st1 = fast_span(g, d1, j1, force_exact, lo1, hi1);
-                if (!has0) st0 = kEmpty;
-                if (!has1) st1 = kEmpty;
-                if (st0 == kSlow) {
-                    slow_item(g, xr, N, c0, j0, (d0.flags & 1u) || force_exact, lo0, hi0);
-                    if (lo0 <= hi0) st0 = kSpan;
-                    else { st0 = kEmpty; lo0 = hi0 = 1; }
-                }
-                if (st1 == kSlow) {
-                    slow_item(g, xr, N, c1, j1, (d1.flags & 1u) || force_exact, lo1, hi1);
-                    if (lo1 <= hi1) st1 = kSpan;
-                    else { st1 = kEmpty; lo1 = hi1 = 1; }
-                }
-                paint_span<MULTI, false>(g, fb, g.planes, j0, lo0, hi0, st0 == kSpan, true, cnt, jb0);
-                paint_span<MULTI, false>(g, fb, g.planes, j1, lo1, hi1, st1 == kSpan, true, cnt, jb0);
             }
             __syncthreads();
-            // clear the band for the next band / candidate
-            const int used = (jb1 - jb0 + 1) * g.stride;
-            for (int t = tid; t < (used + 3) / 4; t += kCtaThreads)
-                reinterpret_cast<uint4 *>(fb)[t] = make_uint4(0, 0, 0, 0);
+            if (units != 0) {
+                // clear the band for the next band / candidate
+                const int used = (jb1 - jb0 + 1) * g.stride;
+                for (int t = tid; t < (used + 3) / 4; t += kCtaThreads)
+                    reinterpret_cast<uint4 *>(fb)[t] = make_uint4(0, 0, 0, 0);
+            }
 #pragma unroll
             for (int k = 0; k < (MULTI ? kMaxClasses : 1); ++k) { // keep 32-bit partials far from overflow
                 cls_total[k] += cnt[k];
                 cnt[k] = 0;
             }
-            __syncthreads();
+            // the next band's prefix writes wait for everyone at the __syncthreads above; the clear is
+            // ordered against the next band's painting by the __syncthreads after its prefix scan
         }
 
         // ---- E. reduce the counts, assemble, write ----
 #pragma unroll
         for (int k = 0; k < (MULTI ? kMaxClasses : 1); ++k) {
-            // per-thread totals fit 32 bits per band but not necessarily overall: reduce as 64-bit halves
-            unsigned long long v = (unsigned long long)cls_total[k];
+            unsigned long long v = cls_total[k];
             for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-            if (lane == 0) reinterpret_cast<unsigned long long *>(scratch + 512)[warp * kMaxClasses + k] = v;
+            if (lane == 0) s_cnt[warp * kMaxClasses + k] = v;
         }
         __syncthreads();
         if (tid == 0) {
@@ -255,8 +261,7 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
             for (int k = 0; k < kMaxClasses; ++k) {
                 tot[k] = 0;
                 if (k < (MULTI ? kMaxClasses : 1))
-                    for (int w = 0; w < nwarps; ++w)
-                        tot[k] += (long long)reinterpret_cast<unsigned long long *>(scratch + 512)[w * kMaxClasses + k];
+                    for (int w = 0; w < nwarps; ++w) tot[k] += (long long)s_cnt[w * kMaxClasses + k];
                 total_cnt += tot[k];
             }
             out.obj[cand] = assemble_objective(g, o, tot, *s_viol);
@@ -267,17 +272,16 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
                 for (int k = 0; k < g.n_classes; ++k) out.class_count[cand * g.n_classes + k] = tot[k];
         }
     }
-    (void)s_cnt;
 }
 
 cudaError_t launch_span_cta(const GridDesc &g, const ObjParams &o, const LaunchCfg &cfg, const double *dX,
                             long long B, const EvalOut &out, unsigned long long *counter, cudaStream_t stream,
                             LaunchInfo *info)
 {
-    const CtaPlan p = cta_plan(g, o.N, cfg.max_smem_optin, cfg.band_rows);
+    const CtaPlan p = cta_plan(g, o.N, cfg.max_smem_optin + 1024, cfg.band_rows, cfg.ctas_per_sm);
     if (p.band_rows < 1) return cudaErrorInvalidConfiguration;
     const bool multi = !(g.n_planes == 1 && g.n_classes == 1 && g.plane_mult[0] == 1);
-    const int grid = (int)std::min<long long>(B, (long long)cfg.num_sms);
+    const int grid = (int)std::min<long long>(B, (long long)cfg.num_sms * p.ctas_per_sm);
     if (info) {
         info->grid = grid;
         info->block = kCtaThreads;
