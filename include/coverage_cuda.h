@@ -134,6 +134,22 @@ COV_API int cov_get_grid_cells(cov_handle *h, uint8_t *mult);
  * ([x;y;R], 3N doubles) from the device-resident cell store. removed (nullable) = entries deleted. */
 COV_API int cov_remove_covered(cov_handle *h, const double *xyR, int64_t N, int64_t *removed);
 
+/* ---- forest-fire cellular automaton on the device (replaces the offline generator
+ *      src/DynamicArea.jl:17-86 and its xlsx hand-off :100-108 to CellFunctions.update_POI) ----------
+ * state: nx*ny bytes indexed (i-1) + nx*(j-1) like grid[i, j]: 0 = EMPTY, 1 = TREE, 2 = FIRE.
+ * cov_fire_init uploads it and re-creates the cell store on the same lattice (weight dx*dy); with
+ * push_initial != 0 every burning cell becomes one list entry (the reference's initial_points).
+ * cov_fire_step is one update_grid(): each interior TREE cell draws once per burning Moore
+ * neighbour, `wind_speed*cos(wind_direction - atan(2-b, 2-a))*prob_spread > u`, u from
+ * Philox4x32-10 keyed by seed with counter (cell, step, neighbour); every success pushes one list
+ * entry (append != 0: straight into the device-resident store; multiplicities add up like the
+ * duplicates of FirePoints.xlsx). n_pushed (nullable) = entries pushed by this step. */
+COV_API int cov_fire_init(cov_handle *h, int64_t nx, int64_t ny, double dx, double dy, const uint8_t *state,
+                          int32_t push_initial);
+COV_API int cov_fire_step(cov_handle *h, double wind_speed, double wind_direction, double prob_spread,
+                          uint64_t seed, int64_t step, int32_t append, int64_t *n_pushed);
+COV_API int cov_fire_get_state(cov_handle *h, uint8_t *state);
+
 /* ---- objective and constraint parameters (the closures' captured variables:
  *      createObjective(cells, N, r_max) src/TDM_STATIC_opt.jl:82, create_cons3(pre, FOV, d_lim)
  *      src/TDM_Constraints.jl:54, cons8's 15.0 :163, cons7 :142-154) --------------------------- */

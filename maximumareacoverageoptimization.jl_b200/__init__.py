@@ -15,7 +15,7 @@ from ._lib import CoverageError, KERNEL_AUTO, KERNEL_SPAN, KERNEL_BRUTE, KERNEL_
 from ._lib import OPT_KERNEL, OPT_WARPS_PER_CTA, OPT_CTAS_PER_SM, OPT_BAND_ROWS, OPT_FORCE_EXACT, OPT_CHUNK  # noqa: F401
 from .engine import CoverageEngine, TAN_HALF_FOV_DEFAULT, threshold, limits, device_count  # noqa: F401
 from . import AreaCoverageCalculation, CellFunctions, TDM_Constraints, TDM_STATIC_opt, Base_Functions  # noqa: F401
-from . import fire_io, synth, mads, FullSimulation  # noqa: F401
+from . import fire_io, synth, mads, FullSimulation, DynamicArea  # noqa: F401
 
 __all__ = ["CoverageEngine", "CoverageError", "AreaCoverageCalculation", "CellFunctions", "TDM_Constraints",
-           "TDM_STATIC_opt", "Base_Functions", "FullSimulation", "mads", "fire_io", "synth", "threshold", "limits", "device_count"]
+           "TDM_STATIC_opt", "Base_Functions", "FullSimulation", "DynamicArea", "mads", "fire_io", "synth", "threshold", "limits", "device_count"]

@@ -55,6 +55,9 @@ SIGNATURES = {
     "cov_get_grid_info": (_i, [_vp, C.POINTER(GridInfo)]),
     "cov_get_grid_cells": (_i, [_vp, _vp]),
     "cov_remove_covered": (_i, [_vp, _vp, _i64, _pi64]),
+    "cov_fire_init": (_i, [_vp, _i64, _i64, _d, _d, _vp, C.c_int32]),
+    "cov_fire_step": (_i, [_vp, _d, _d, _d, C.c_uint64, _i64, C.c_int32, _pi64]),
+    "cov_fire_get_state": (_i, [_vp, _vp]),
     "cov_set_params": (_i, [_vp, _i64, _vp, _d, _vp, _vp, _d, _d, C.c_int32]),
     "cov_eval_batch": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "cov_eval_batch_ex": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),

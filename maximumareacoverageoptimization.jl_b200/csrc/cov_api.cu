@@ -50,6 +50,10 @@ struct cov_handle {
 
     // scratch
     DevBuf counter, stats, xyT, small_in, argmin_obj, argmin_idx, removed, overflow;
+    // forest-fire automaton state (ping-pong) and its direction probabilities
+    DevBuf fire[2], fire_p;
+    int fire_cur = 0;
+    bool have_fire = false;
     // evaluation window (device) and staging (pinned host)
     DevBuf dX, d_obj, d_count, d_feas, d_clscnt, d_prog;
     void *h_in[2] = {nullptr, nullptr};
@@ -278,7 +282,7 @@ extern "C" void cov_destroy(cov_handle *h)
     cudaStreamSynchronize(h->s_out);
     DevBuf *bufs[] = {&h->mult, &h->cls, &h->planes, &h->params, &h->counter, &h->stats, &h->xyT,
                       &h->small_in, &h->argmin_obj, &h->argmin_idx, &h->removed, &h->overflow, &h->dX,
-                      &h->d_obj, &h->d_count, &h->d_feas, &h->d_clscnt, &h->d_prog};
+                      &h->d_obj, &h->d_count, &h->d_feas, &h->d_clscnt, &h->d_prog, &h->fire[0], &h->fire[1], &h->fire_p};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (int k = 0; k < 2; ++k)
@@ -752,6 +756,91 @@ extern "C" int cov_covered_mask(cov_handle *h, const double *x, uint8_t *mask)
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     cudaFree(dm.p);
     if (e != cudaSuccess) return fail_cuda(h, e, "cov_covered_mask");
+    return COV_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// forest-fire automaton (src/DynamicArea.jl of the reference) feeding the cell store directly
+// ------------------------------------------------------------------------------------------
+extern "C" int cov_fire_init(cov_handle *h, int64_t nx, int64_t ny, double dx, double dy, const uint8_t *state,
+                             int32_t push_initial)
+{
+    if (!h) return fail(nullptr, COV_ERR_INVALID, "NULL handle");
+    DeviceGuard dg(h->device);
+    if (!state) return fail(h, COV_ERR_INVALID, "cov_fire_init: state is NULL");
+    OK(check_lattice(h, nx, ny, dx, dy));
+    const size_t ncell = (size_t)nx * ny;
+    for (size_t t = 0; t < ncell; ++t)
+        if (state[t] > 2) return fail(h, COV_ERR_INVALID, "cov_fire_init: cell states must be 0 (empty), 1 (tree), 2 (fire)");
+    h->have_grid = false;
+    h->have_fire = false;
+    describe_lattice(h, nx, ny, dx, dy);
+    OK(alloc_cells(h));
+    OK(ensure(h, h->fire[0], ncell));
+    OK(ensure(h, h->fire[1], ncell));
+    OK(ensure(h, h->fire_p, 9 * sizeof(double)));
+    CK(cudaMemcpyAsync(h->fire[0].p, state, ncell, cudaMemcpyHostToDevice, h->stream));
+    CK(launch_fire_seed((const unsigned char *)h->fire[0].p, (unsigned char *)h->mult.p, (unsigned char *)h->cls.p,
+                        (long long)ncell, push_initial, h->stream));
+    h->launches += 1;
+    CK(cudaStreamSynchronize(h->stream));
+    h->fire_cur = 0;
+    h->have_fire = true;
+    const double w = dx * dy; // DynamicArea.jl:65: area = weight = dx*dy
+    return rebuild_planes(h, 1, &w);
+}
+
+extern "C" int cov_fire_step(cov_handle *h, double wind_speed, double wind_direction, double prob_spread,
+                             uint64_t seed, int64_t step, int32_t append, int64_t *n_pushed)
+{
+    if (!h) return fail(nullptr, COV_ERR_INVALID, "NULL handle");
+    DeviceGuard dg(h->device);
+    if (!h->have_fire) return fail(h, COV_ERR_STATE, "cov_fire_step: cov_fire_init has not been called");
+    if (step < 0 || step > 0xffffffffll) return fail(h, COV_ERR_INVALID, "cov_fire_step: step out of range");
+    if (h->g.n_classes != 1)
+        return fail(h, COV_ERR_STATE, "cov_fire_step: the cell store holds several weight classes");
+    // the probability of ignition from the neighbour at window index (a, b), a, b = 1..3, exactly as the
+    // reference forms it: wind_speed * cos(wind_direction - atan(2-b, 2-a)) * prob_spread
+    double *hp = (double *)h->h_small + 64;
+    for (int b = 1; b <= 3; ++b)
+        for (int a = 1; a <= 3; ++a) {
+            volatile double ang = atan2((double)(2 - b), (double)(2 - a));
+            volatile double c = cos(wind_direction - ang);
+            volatile double p = wind_speed * c;
+            hp[(a - 1) + 3 * (b - 1)] = p * prob_spread;
+        }
+    CK(cudaMemcpyAsync(h->fire_p.p, hp, 9 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->removed.p, 0, sizeof(unsigned long long), h->stream));
+    CK(cudaMemsetAsync(h->overflow.p, 0, sizeof(int), h->stream));
+    const int cur = h->fire_cur;
+    CK(launch_fire_step((const unsigned char *)h->fire[cur].p, (unsigned char *)h->fire[cur ^ 1].p,
+                        (unsigned char *)h->mult.p, (unsigned char *)h->cls.p, h->g.nx, h->g.ny, seed,
+                        (unsigned int)step, (const double *)h->fire_p.p, append, (unsigned long long *)h->removed.p,
+                        (int *)h->overflow.p, h->stream));
+    h->launches += 1;
+    unsigned long long *hr = (unsigned long long *)h->h_small + 16;
+    int *hov = (int *)h->h_small;
+    CK(cudaMemcpyAsync(hr, h->removed.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(hov, h->overflow.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->fire_cur = cur ^ 1;
+    if (n_pushed) *n_pushed = (int64_t)*hr;
+    if (*hov) return fail(h, COV_ERR_LIMIT, "more than 255 list entries on one cell");
+    if (!append || *hr == 0) return COV_OK;
+    double cw[kMaxClasses];
+    for (int k = 0; k < kMaxClasses; ++k) cw[k] = h->g.class_weight[k];
+    return rebuild_planes(h, 1, cw);
+}
+
+extern "C" int cov_fire_get_state(cov_handle *h, uint8_t *state)
+{
+    if (!h) return fail(nullptr, COV_ERR_INVALID, "NULL handle");
+    DeviceGuard dg(h->device);
+    if (!h->have_fire) return fail(h, COV_ERR_STATE, "cov_fire_get_state: cov_fire_init has not been called");
+    if (!state) return fail(h, COV_ERR_INVALID, "NULL output");
+    CK(cudaMemcpyAsync(state, h->fire[h->fire_cur].p, (size_t)h->g.nx * h->g.ny, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return COV_OK;
 }
 

@@ -397,6 +397,62 @@ __device__ __forceinline__ double u01_53(uint32_t a, uint32_t b)
     const unsigned long long v = ((unsigned long long)(a >> 5) << 26) | (unsigned long long)(b >> 6);
     return __dmul_rn((double)v, 1.1102230246251565e-16); // 2^-53
 }
+// ---- forest-fire cellular automaton on the device (src/DynamicArea.jl:52-72 of /root/reference) ----
+// One thread per interior cell.  A TREE cell with burning Moore neighbours draws once PER burning
+// neighbour, window index (a, b) iterated column-major like findall; a success sets FIRE and pushes
+// one list entry (so a cell can be pushed several times in a step: the duplicates of FirePoints.xlsx).
+// rand() is replaced by a counter-based uniform: Philox4x32-10 with counter
+// (cell index, step, neighbour index k = (a-1) + 3(b-1), 0) and key = seed.
+__global__ void fire_step_kernel(const unsigned char *__restrict__ cur, unsigned char *__restrict__ nxt,
+                                 unsigned char *mult, unsigned char *cls, int nx, int ny, unsigned long long seed,
+                                 unsigned int step, const double *__restrict__ p_dir, int append,
+                                 unsigned long long *pushed, int *overflow)
+{
+    const long long ncell = (long long)nx * ny;
+    unsigned long long mine = 0;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < ncell;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t % nx) + 1, j = (int)(t / nx) + 1; // 1-based grid[i, j]
+        unsigned char st = cur[t];
+        unsigned pushes = 0;
+        if (st == 1 && i >= 2 && i <= nx - 1 && j >= 2 && j <= ny - 1) {
+            for (int b = 1; b <= 3; ++b)
+                for (int a = 1; a <= 3; ++a) {
+                    const long long nb = (long long)(i - 2 + a - 1) + (long long)nx * (j - 2 + b - 1);
+                    if (cur[nb] != 2) continue;
+                    const int k = (a - 1) + 3 * (b - 1);
+                    uint32_t r[4];
+                    philox4x32_10((uint32_t)t, step, (uint32_t)k, (uint32_t)((unsigned long long)t >> 32),
+                                  (uint32_t)seed, (uint32_t)(seed >> 32), r);
+                    if (p_dir[k] > u01_53(r[0], r[1])) ++pushes;
+                }
+            if (pushes) st = 2;
+        }
+        nxt[t] = st;
+        if (pushes && append) {
+            const unsigned m = mult[t] + pushes; // one thread per cell: no race
+            if (m > 255u) atomicExch(overflow, 1);
+            mult[t] = (unsigned char)(m > 255u ? 255u : m);
+            cls[t] = 0;
+        }
+        mine += pushes;
+    }
+    for (int off = 16; off; off >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, off);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(pushed, mine);
+}
+
+// initial state -> the list entries of the ignition cells (src/DynamicArea.jl:37-43)
+__global__ void fire_seed_kernel(const unsigned char *__restrict__ state, unsigned char *mult, unsigned char *cls,
+                                 long long ncell, int push_initial)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < ncell;
+         t += (long long)gridDim.x * blockDim.x) {
+        const bool burning = push_initial && state[t] == 2;
+        mult[t] = burning ? 1 : 0;
+        cls[t] = burning ? 0 : 0xffu;
+    }
+}
+
 __global__ void generate_kernel(double *X, long long B, int N, unsigned long long seed, long long first, double lx,
                                 double ly, double h_min, double h_max, double tan_half_fov)
 {
@@ -426,6 +482,26 @@ cudaError_t launch_generate(double *dX, long long B, int N, unsigned long long s
     const int block = 256;
     const int grid = (int)std::min<long long>((B * N + block - 1) / block, 148 * 16);
     generate_kernel<<<grid, block, 0, s>>>(dX, B, N, seed, first, lx, ly, h_min, h_max, tan_half_fov);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fire_step(const unsigned char *cur, unsigned char *nxt, unsigned char *mult, unsigned char *cls,
+                             int nx, int ny, unsigned long long seed, unsigned int step, const double *p_dir,
+                             int append, unsigned long long *pushed, int *overflow, cudaStream_t s)
+{
+    const long long ncell = (long long)nx * ny;
+    const int block = 256;
+    const int grid = (int)std::min<long long>((ncell + block - 1) / block, 148 * 8);
+    fire_step_kernel<<<max(grid, 1), block, 0, s>>>(cur, nxt, mult, cls, nx, ny, seed, step, p_dir, append, pushed,
+                                                    overflow);
+    return cudaGetLastError();
+}
+cudaError_t launch_fire_seed(const unsigned char *state, unsigned char *mult, unsigned char *cls, long long ncell,
+                             int push_initial, cudaStream_t s)
+{
+    const int block = 256;
+    const int grid = (int)std::min<long long>((ncell + block - 1) / block, 148 * 8);
+    fire_seed_kernel<<<max(grid, 1), block, 0, s>>>(state, mult, cls, ncell, push_initial);
     return cudaGetLastError();
 }
 

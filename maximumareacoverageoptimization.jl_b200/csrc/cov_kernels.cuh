@@ -57,6 +57,11 @@ cudaError_t launch_add_points(unsigned char *mult, unsigned char *cls, const int
                               const unsigned char *cell_cls, long long P, int *overflow, cudaStream_t s);
 cudaError_t launch_argmin(const double *obj, const unsigned char *feasible, long long B, int barrier,
                           double *scratch_obj, long long *scratch_idx, int scratch_n, cudaStream_t s);
+cudaError_t launch_fire_step(const unsigned char *cur, unsigned char *nxt, unsigned char *mult, unsigned char *cls,
+                             int nx, int ny, unsigned long long seed, unsigned int step, const double *p_dir,
+                             int append, unsigned long long *pushed, int *overflow, cudaStream_t s);
+cudaError_t launch_fire_seed(const unsigned char *state, unsigned char *mult, unsigned char *cls, long long ncell,
+                             int push_initial, cudaStream_t s);
 cudaError_t launch_generate(double *dX, long long B, int N, unsigned long long seed, long long first,
                             double lx, double ly, double h_min, double h_max, double tan_half_fov,
                             cudaStream_t s);

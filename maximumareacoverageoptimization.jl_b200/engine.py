@@ -164,6 +164,27 @@ class CoverageEngine:
         self._check(lib.cov_covered_mask(self._h, _ptr(x), _ptr(out)))
         return out
 
+    # ---- forest-fire automaton (src/DynamicArea.jl) ----
+    def fire_init(self, state: np.ndarray, nx: int, ny: int, dx: float, dy: float, push_initial: bool = True):
+        """state: nx*ny bytes (0 EMPTY, 1 TREE, 2 FIRE) indexed (i-1) + nx*(j-1)."""
+        state = np.ascontiguousarray(state, dtype=np.uint8).ravel()
+        if state.size != nx * ny:
+            raise ValueError("state must hold nx*ny bytes")
+        self._check(lib.cov_fire_init(self._h, nx, ny, dx, dy, _ptr(state), 1 if push_initial else 0))
+
+    def fire_step(self, wind_speed: float, wind_direction: float, prob_spread: float, seed: int, step: int,
+                  append: bool = True) -> int:
+        n = C.c_int64()
+        self._check(lib.cov_fire_step(self._h, wind_speed, wind_direction, prob_spread, seed, step,
+                                      1 if append else 0, C.byref(n)))
+        return n.value
+
+    def fire_state(self) -> np.ndarray:
+        gi = self.grid_info()
+        out = np.empty(gi["nx"] * gi["ny"], dtype=np.uint8)
+        self._check(lib.cov_fire_get_state(self._h, _ptr(out)))
+        return out
+
     # ---- parameters ----
     def set_params(self, N: int, r_max, penalty_scale: float = 1e5, prev_xyR=None, d_lim=None,
                    tan_half_fov: float = TAN_HALF_FOV_DEFAULT, sep_min: float = 0.0, use_cons7: bool = False):

@@ -57,6 +57,8 @@ def lib():
         L.orc_eval_batch.argtypes = [_vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _d, _d, _i, _vp, _vp, _vp, _vp, _i]
         L.orc_class_counts.restype = None
         L.orc_class_counts.argtypes = [_vp, _i64, _vp, _i64, _vp, _i64, _vp]
+        L.orc_fire_step_philox.restype = _i64
+        L.orc_fire_step_philox.argtypes = [_vp, _vp, _i64, _i64, _d, _d, _d, _d, _d, _i64, C.c_uint64, _vp]
         L.orc_threshold_by_search.restype = _d
         L.orc_threshold_by_search.argtypes = [_d]
         L.orc_num_threads.restype = _i
@@ -148,6 +150,18 @@ def class_counts(circles, pts5, class_of, n_classes):
     out = np.zeros(n_classes, dtype=np.int64)
     lib().orc_class_counts(_p(circles), circles.size // 3, _p(pts5), pts5.shape[0], _p(class_of), n_classes, _p(out))
     return out
+
+
+def fire_step(grid, nx, ny, dx, dy, wind_speed, wind_direction, prob_spread, step, seed):
+    """One update_grid() step; grid: nx*ny uint8 (index (i-1) + nx*(j-1)). Returns (new_grid, pts5)."""
+    grid = np.ascontiguousarray(grid, dtype=np.uint8).ravel()
+    new = np.empty_like(grid)
+    n = lib().orc_fire_step_philox(_p(grid), _p(new), nx, ny, dx, dy, wind_speed, wind_direction, prob_spread,
+                                   step, seed, None)
+    pts = np.empty((n, 5), dtype=np.float64)
+    lib().orc_fire_step_philox(_p(grid), _p(new), nx, ny, dx, dy, wind_speed, wind_direction, prob_spread,
+                               step, seed, _p(pts))
+    return new, pts
 
 
 def threshold_by_search(R: float) -> float:

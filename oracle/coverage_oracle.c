@@ -349,6 +349,49 @@ ORC_API int64_t orc_fire_update_grid(const uint8_t *grid, uint8_t *new_grid, int
     return n;
 }
 
+/* Counter-based uniform for the fire automaton: Philox4x32-10 (Salmon et al., SC'11) with counter
+ * (cell index low 32, step, neighbour index k = (a-1) + 3(b-1), cell index high 32) and key = seed;
+ * 53 bits -> [0, 1).  The device kernel (cov_grid_kernels.cu fire_step_kernel) draws the same. */
+static void orc_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                              uint32_t out[4])
+{
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+typedef struct orc_philox_ctx {
+    uint64_t seed;
+    int64_t nx;
+} orc_philox_ctx;
+
+static double orc_philox_u01(void *vctx, int64_t step, int64_t i, int64_t j, int a, int b)
+{
+    const orc_philox_ctx *ctx = (const orc_philox_ctx *)vctx;
+    const uint64_t cell = (uint64_t)((i - 1) + ctx->nx * (j - 1));
+    uint32_t r[4];
+    orc_philox4x32_10((uint32_t)cell, (uint32_t)step, (uint32_t)((a - 1) + 3 * (b - 1)), (uint32_t)(cell >> 32),
+                      (uint32_t)ctx->seed, (uint32_t)(ctx->seed >> 32), r);
+    const uint64_t v = ((uint64_t)(r[0] >> 5) << 26) | (uint64_t)(r[1] >> 6);
+    return (double)v * 1.1102230246251565e-16; /* 2^-53 */
+}
+
+/* One update_grid() step (src/DynamicArea.jl:52-72) with the Philox uniforms above. */
+ORC_API int64_t orc_fire_step_philox(const uint8_t *grid, uint8_t *new_grid, int64_t nx, int64_t ny, double dx,
+                                     double dy, double wind_speed, double wind_direction, double prob_spread,
+                                     int64_t step, uint64_t seed, double *pts5)
+{
+    orc_philox_ctx ctx = {seed, nx};
+    return orc_fire_update_grid(grid, new_grid, nx, ny, dx, dy, wind_speed, wind_direction, prob_spread, step,
+                                orc_philox_u01, &ctx, pts5);
+}
+
 /* Threshold identity used by the CUDA kernels, stated here by its DEFINITION so tests can check
  * the device's closed form against it:  T(R) = the smallest double t (possibly +Inf) with
  * sqrt(t) >= R, so that for every double s >= 0:  sqrt(s) < R  <=>  s < T(R)

@@ -601,3 +601,38 @@ def test_receding_horizon_fire_c5(cov, orc, fire_rows):
         pre = outp[t - 1]
     assert np.array_equal(cells.points_of_interest.data, ref)
     cells.close()
+
+
+# ---------------------------------------------------------------- forest-fire automaton on the device
+def test_fire_automaton_matches_oracle(cov, orc, engine):
+    """DynamicArea.jl's update_grid on the device: grid state and the pushed list entries (with their
+    duplicates) equal the C restatement fed with the same Philox uniforms, step by step; then the
+    objective on the device-grown store equals the oracle on the replayed list."""
+    ff = cov.DynamicArea.ForestFire(engine, seed=2026)
+    nx, ny = ff.nx, ff.ny
+    assert (nx, ny) == (100, 100)
+    grid = ff.initial_grid.T.ravel().copy()
+    ii, jj = np.nonzero(ff.initial_grid == 2)
+    order = np.lexsort((ii, jj))  # DynamicArea.jl:38-42: y outer, x inner
+    pts = np.stack([(ii[order] + 1) * 5.0 - 2.5, (jj[order] + 1) * 5.0 - 2.5, np.full(len(ii), 25.0),
+                    np.full(len(ii), 25.0), np.zeros(len(ii))], axis=1)
+    assert engine.grid_info()["n_entries"] == len(pts) == 21 * 3
+    total_dups = 0
+    for step in range(1, 41):
+        pushed = ff.step()
+        grid, new_pts = orc.fire_step(grid, nx, ny, 5.0, 5.0, 4.0, math.radians(270.0), 0.5, step, 2026)
+        assert pushed == len(new_pts)
+        pts = np.concatenate([pts, new_pts])
+        assert np.array_equal(engine.fire_state(), grid)
+        total_dups += len(new_pts) - len(np.unique(new_pts[:, :2], axis=0))
+    assert total_dups > 0  # cells pushed more than once in a step, as in FirePoints.xlsx
+    ref_mult = np.zeros(nx * ny, dtype=np.int64)
+    np.add.at(ref_mult, cov.AreaCoverageCalculation.PointList(pts, nx, ny, 5.0, 5.0).cell_index(), 1)
+    assert np.array_equal(engine.grid_cells(), ref_mult)
+    N = 5
+    r_max = np.full(N, 30 * T)
+    engine.set_params(N, r_max)
+    rng = np.random.default_rng(12)
+    X = rand_candidates(rng, 1000, N)
+    X[:, N:2 * N] *= 0.8
+    check_against_oracle(cov, orc, engine, X, N, r_max, pts)
