@@ -125,18 +125,20 @@ __device__ __forceinline__ int fast_span(const GridDesc &g, const SDisc &d, int 
     const float w = w2 > 0.0f ? w2 * rsqrtf(w2) : 0.0f; // an estimate only: the ends are certified below
     const float ulo = ceilf((d.fx - w) * g.inv_dxf);
     const float uhi = floorf((d.fx + w) * g.inv_dxf);
+    // estimate says "no cell" (a chord shorter than the cell pitch): probe the cell left of the centre
+    // and its right neighbour instead; both certainly outside proves the row empty, because they are
+    // at least as close to the centre as any in-grid cell
     const bool est_empty = ulo > uhi;
-    // estimate says "no cell": certain if the two cells around the centre are certainly outside
     const float ua = floorf(d.fx * g.inv_dxf);
-    const float xa = fmaf(ua, g.dxf, -d.fx), xb = xa + g.dxf;
-    const bool ok_empty = (fmaf(xa, xa, dy2) > thi) && (fmaf(xb, xb, dy2) > thi);
     const float nxf = int_to_float_small(g.nx);
     const float lof = fmaxf(d.icf + (est_empty ? ua : ulo), 1.0f), hif = fminf(d.icf + (est_empty ? ua : uhi), nxf);
     const float x_lo = fmaf(lof - d.icf, g.dxf, -d.fx), x_hi = fmaf(hif - d.icf, g.dxf, -d.fx);
     const float x_lm = x_lo - g.dxf, x_hp = x_hi + g.dxf;
-    const bool ok_span = (fmaf(x_lo, x_lo, dy2) < tlo) && (fmaf(x_hi, x_hi, dy2) < tlo) &&
-                         (lof == 1.0f || fmaf(x_lm, x_lm, dy2) > thi) && (hif == nxf || fmaf(x_hp, x_hp, dy2) > thi) &&
+    const float s_lo = fmaf(x_lo, x_lo, dy2), s_hi = fmaf(x_hi, x_hi, dy2);
+    const float s_lm = fmaf(x_lm, x_lm, dy2), s_hp = fmaf(x_hp, x_hp, dy2);
+    const bool ok_span = (s_lo < tlo) && (s_hi < tlo) && (lof == 1.0f || s_lm > thi) && (hif == nxf || s_hp > thi) &&
                          (lof <= hif);
+    const bool ok_empty = (s_lo > thi) && (s_hp > thi);
     lo = (int)fminf(lof, nxf);
     hi = (int)fmaxf(hif, 1.0f);
     const bool irregular = (d.flags & 1u) || force_exact;
@@ -179,7 +181,10 @@ __device__ __forceinline__ void count_word(const GridDesc &g, const uint32_t *pw
 
 // valid = false paints nothing (lets two items share one straight-line instruction stream).
 // fb_row0: the 1-based grid row held by framebuffer row 0 (banded framebuffers).
-template <bool MULTI, bool PLANES_SMEM = true>
+// valid = false paints nothing (lets several items share one straight-line instruction stream).
+// The first word, the last word and (WIDE) one word in between are handled without branches; any
+// further whole words in a loop.
+template <bool MULTI, bool PLANES_SMEM = true, bool WIDE = false>
 __device__ __forceinline__ void paint_span(const GridDesc &g, uint32_t *fb, const uint32_t *planes, int j, int lo,
                                            int hi, bool valid, bool shared, uint32_t *cnt, int fb_row0 = 1)
 {
@@ -187,29 +192,27 @@ __device__ __forceinline__ void paint_span(const GridDesc &g, uint32_t *fb, cons
     const int wa = a >> 5, wb = b >> 5;
     uint32_t *frow = fb + (j - fb_row0) * g.stride;
     const uint32_t *prow = planes + (size_t)(j - 1) * g.stride;
-    const uint32_t ma = valid ? 0xffffffffu << (a & 31) : 0u, mb = 0xffffffffu >> (31 - (b & 31));
-    // the first three words without branches (a span of the bench workload touches at most three)
-    const int w1 = min(wa + 1, wb), w2 = min(wa + 2, wb);
+    const uint32_t ma = 0xffffffffu << (a & 31), mb = 0xffffffffu >> (31 - (b & 31));
     uint32_t m0 = (wa == wb) ? (ma & mb) : ma;
-    uint32_t m1 = (wb == wa) ? 0u : ((wb == wa + 1) ? mb : 0xffffffffu);
-    uint32_t m2 = (wb <= wa + 1) ? 0u : ((wb == wa + 2) ? mb : 0xffffffffu);
-    if (!valid) m1 = m2 = 0u;
+    uint32_t m1 = (wa == wb) ? 0u : mb;
+    const int wm = min(wa + 1, wb);
+    uint32_t m2 = (WIDE && wb > wa + 1) ? 0xffffffffu : 0u;
+    if (!valid) m0 = m1 = m2 = 0u;
     if (shared) {
         if (m0) m0 &= ~atomicOr(frow + wa, m0);
-        if (m1) m1 &= ~atomicOr(frow + w1, m1);
-        if (m2) m2 &= ~atomicOr(frow + w2, m2);
+        if (m1) m1 &= ~atomicOr(frow + wb, m1);
+        if (WIDE && m2) m2 &= ~atomicOr(frow + wm, m2);
     }
     count_word<MULTI, PLANES_SMEM>(g, prow + wa, m0, cnt);
-    count_word<MULTI, PLANES_SMEM>(g, prow + w1, m1, cnt);
-    count_word<MULTI, PLANES_SMEM>(g, prow + w2, m2, cnt);
-    if (valid && wb > wa + 2) {
-        for (int w = wa + 3; w <= wb; ++w) {
-            uint32_t m = (w == wb) ? mb : 0xffffffffu;
+    count_word<MULTI, PLANES_SMEM>(g, prow + wb, m1, cnt);
+    if (WIDE) count_word<MULTI, PLANES_SMEM>(g, prow + wm, m2, cnt);
+    if (valid) {
+        for (int w = wa + (WIDE ? 2 : 1); w < wb; ++w) { // whole words in between
+            uint32_t m = 0xffffffffu;
             if (shared) m &= ~atomicOr(frow + w, m);
             count_word<MULTI, PLANES_SMEM>(g, prow + w, m, cnt);
         }
     }
 }
-
 
 } // namespace cov

@@ -227,8 +227,8 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
                         if (lo1 <= hi1) st1 = kSpan;
                         else { st1 = kEmpty; lo1 = hi1 = 1; }
                     }
-                    paint_span<MULTI, false>(g, fb, g.planes, jj0, lo0, hi0, st0 == kSpan, true, cnt, jb0);
-                    paint_span<MULTI, false>(g, fb, g.planes, jj1, lo1, hi1, st1 == kSpan, true, cnt, jb0);
+                    paint_span<MULTI, false, true>(g, fb, g.planes, jj0, lo0, hi0, st0 == kSpan, true, cnt, jb0);
+                    paint_span<MULTI, false, true>(g, fb, g.planes, jj1, lo1, hi1, st1 == kSpan, true, cnt, jb0);
                 }
             }
             __syncthreads();
