@@ -67,7 +67,8 @@ enum {
     COV_OPT_CTAS_PER_SM = 3,    /* 0 = auto */
     COV_OPT_BAND_ROWS = 4,      /* span kernel framebuffer band height in rows; 0 = auto */
     COV_OPT_FORCE_EXACT = 5,    /* 1: span/brute kernels skip the FP32 band and decide every edge in FP64 */
-    COV_OPT_CHUNK = 6           /* host-path pipeline chunk (candidates per H2D/launch/D2H slice); 0 = auto */
+    COV_OPT_CHUNK = 6,          /* host-path pipeline chunk (candidates per H2D/launch/D2H slice); 0 = auto */
+    COV_OPT_TRACE = 7           /* 1: record a per-slice device timeline of every host-path call (cov_get_trace) */
 };
 
 typedef struct cov_handle cov_handle;
@@ -205,6 +206,10 @@ COV_API int cov_memcpy_h2d(cov_handle *h, void *dst, const void *src, int64_t by
 COV_API int cov_memcpy_d2h(cov_handle *h, void *dst, const void *src, int64_t bytes); /* async on the stream */
 /* Kernel launches issued by this handle since creation (evidence for bench.py's gpu_launches). */
 COV_API int64_t cov_launch_count(const cov_handle *h);
+/* Timeline of the last host-path call recorded under COV_OPT_TRACE: per slice the device times (ms since
+ * the call's first copy was queued) of: H2D done, kernel start, kernel end, D2H done. Returns the number of
+ * values available; copies at most cap of them. */
+COV_API int64_t cov_get_trace(const cov_handle *h, double *ms, int64_t cap);
 /* Device time of the last cov_eval_batch* coverage-kernel launch(es) in milliseconds, measured
  * with CUDA events on the handle's stream (synchronises). */
 COV_API int cov_last_kernel_ms(cov_handle *h, double *ms);

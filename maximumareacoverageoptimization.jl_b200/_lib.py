@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcoverage_cuda.so")
+LIB_PATH = os.environ.get("COVERAGE_CUDA_LIB") or os.path.join(_HERE, "libcoverage_cuda.so")  # override: kernel experiments
 
 COV_OK = 0
 COV_ERR_INVALID = -1
@@ -21,7 +21,7 @@ COV_ERR_LIMIT = -5
 COV_ERR_NOMEM = -6
 
 KERNEL_AUTO, KERNEL_SPAN, KERNEL_BRUTE, KERNEL_EXACT, KERNEL_SPAN_GENERAL = 0, 1, 2, 3, 4
-OPT_KERNEL, OPT_WARPS_PER_CTA, OPT_CTAS_PER_SM, OPT_BAND_ROWS, OPT_FORCE_EXACT, OPT_CHUNK = 1, 2, 3, 4, 5, 6
+OPT_KERNEL, OPT_WARPS_PER_CTA, OPT_CTAS_PER_SM, OPT_BAND_ROWS, OPT_FORCE_EXACT, OPT_CHUNK, OPT_TRACE = 1, 2, 3, 4, 5, 6, 7
 
 
 class GridInfo(C.Structure):
@@ -75,6 +75,7 @@ SIGNATURES = {
     "cov_memcpy_h2d": (_i, [_vp, _vp, _vp, _i64]),
     "cov_memcpy_d2h": (_i, [_vp, _vp, _vp, _i64]),
     "cov_launch_count": (_i64, [_vp]),
+    "cov_get_trace": (_i64, [_vp, _pd, _i64]),
     "cov_last_kernel_ms": (_i, [_vp, _pd]),
     "cov_kernel_time_total": (_i, [_vp, _pd, _pi64]),
     "cov_generate_candidates": (_i, [_vp, _vp, _i64, _i64, C.c_uint64, _i64, _d, _d, _d, _d, _d]),

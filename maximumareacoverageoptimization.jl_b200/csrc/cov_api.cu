@@ -71,9 +71,15 @@ struct cov_handle {
     double last_call_ms_cache = -1;
     int64_t launches = 0;
     LaunchInfo last_info{};
+    int counter_next = 0; // next unused slot of the zeroed counter ring
+    // COV_OPT_TRACE: per-slice timeline of the last host-path call (ms since its first copy was queued)
+    int trace = 0;
+    std::vector<cudaEvent_t> trace_ev; // start, then per slice: h2d done, kernel start, kernel end, d2h done
+    std::vector<double> trace_ms;
 };
 
 static thread_local std::string g_err_nohandle;
+constexpr int kCounterSlots = 4096; // work-dispenser counters, zeroed in bulk (one fresh slot per launch)
 
 static int fail(cov_handle *h, int code, const std::string &msg)
 {
@@ -258,7 +264,9 @@ extern "C" int cov_create(int device, cov_handle **out)
     nh->cfg.num_sms = prop.multiProcessorCount;
     nh->cfg.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     if ((e = cudaMallocHost(&nh->h_small, 4096 + 3 * kMaxUavs * 8)) != cudaSuccess) return bail(e, "cudaMallocHost");
-    int rc = ensure(nh, nh->counter, 256);
+    int rc = ensure(nh, nh->counter, kCounterSlots * sizeof(unsigned long long));
+    if (rc == COV_OK && cudaMemset(nh->counter.p, 0, kCounterSlots * sizeof(unsigned long long)) != cudaSuccess)
+        rc = fail_cuda(nh, cudaGetLastError(), "cudaMemset");
     if (rc == COV_OK) rc = ensure(nh, nh->stats, 256);
     if (rc == COV_OK) rc = ensure(nh, nh->removed, 256);
     if (rc == COV_OK) rc = ensure(nh, nh->overflow, 256);
@@ -291,6 +299,7 @@ extern "C" void cov_destroy(cov_handle *h)
     if (h->h_small) cudaFreeHost(h->h_small);
     (void)drain_spans(h);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->trace_ev) cudaEventDestroy(e);
     cudaStreamDestroy(h->s_in);
     cudaStreamDestroy(h->s_out);
     cudaStreamDestroy(h->own_stream);
@@ -327,6 +336,9 @@ extern "C" int cov_set_option(cov_handle *h, int option, int64_t value)
         if (value < 0) return fail(h, COV_ERR_INVALID, "chunk must be >= 0");
         h->chunk = value;
         return COV_OK;
+    case COV_OPT_TRACE:
+        h->trace = value != 0;
+        return COV_OK;
     }
     return fail(h, COV_ERR_INVALID, "unknown option");
 }
@@ -341,6 +353,7 @@ extern "C" int cov_get_option(const cov_handle *h, int option, int64_t *value)
     case COV_OPT_BAND_ROWS: *value = h->cfg.band_rows; return COV_OK;
     case COV_OPT_FORCE_EXACT: *value = h->cfg.force_exact; return COV_OK;
     case COV_OPT_CHUNK: *value = h->chunk; return COV_OK;
+    case COV_OPT_TRACE: *value = h->trace; return COV_OK;
     }
     return COV_ERR_INVALID;
 }
@@ -694,7 +707,7 @@ extern "C" int cov_get_grid_info(const cov_handle *h, cov_grid_info *info)
     info->n_planes = h->g.n_planes;
     info->n_classes = h->g.n_classes;
     info->area_exact = h->area_exact;
-    info->planes_in_smem = span_small_applies(h->g, h->have_params ? h->o.N : 1, h->cfg, nullptr, nullptr) ? 1 : 0;
+    info->planes_in_smem = span_small_applies(h->g, h->have_params ? h->o.N : 1, h->cfg, 0, nullptr, nullptr) ? 1 : 0;
     return COV_OK;
 }
 
@@ -903,7 +916,12 @@ static int launch_on_main(cov_handle *h, const double *dX, int64_t B, const Eval
         e1 = get_event(h);
         CK(cudaEventRecord(e0, h->stream));
     }
-    cudaError_t e = launch_eval(h->g, h->o, h->cfg, dX, (long long)B, out, (unsigned long long *)h->counter.p,
+    if (h->counter_next >= kCounterSlots) { // ring used up: zero it again (stream-ordered after its last user)
+        CK(cudaMemsetAsync(h->counter.p, 0, kCounterSlots * sizeof(unsigned long long), h->stream));
+        h->counter_next = 0;
+    }
+    cudaError_t e = launch_eval(h->g, h->o, h->cfg, dX, (long long)B, out,
+                                (unsigned long long *)h->counter.p + h->counter_next++,
                                 h->stream, &h->last_info);
     if (e != cudaSuccess) {
         if (timed) {
@@ -962,7 +980,8 @@ static int eval_host(cov_handle *h, const double *X, int64_t B, double *obj, int
     const size_t row_bytes = (size_t)3 * N * 8;
     // device window: at most ~1 GiB of candidates at a time
     const int64_t window = std::max<int64_t>(1, std::min<int64_t>(B, (int64_t)((1ull << 30) / row_bytes)));
-    int64_t chunk = h->chunk > 0 ? h->chunk : std::max<int64_t>(1024, (int64_t)((16ull << 20) / row_bytes));
+    // slice size: ~16 MiB of candidates, a multiple of 32 candidates (keeps device slices 16-byte aligned)
+    int64_t chunk = h->chunk > 0 ? h->chunk : std::max<int64_t>(1024, (int64_t)((16ull << 20) / row_bytes) / 32 * 32);
     chunk = std::min(chunk, window);
     OK(ensure(h, h->dX, (size_t)window * row_bytes));
     OK(ensure(h, h->d_obj, (size_t)window * 8));
@@ -1009,11 +1028,26 @@ static int eval_host(cov_handle *h, const double *X, int64_t B, double *obj, int
     // the copy streams must not start before earlier work on the main stream (grid/params) is done
     CKD(cudaEventRecord(ev_k, h->stream));
     CKD(cudaStreamWaitEvent(h->s_in, ev_k, 0));
+    auto tr = [&](cudaStream_t s) {
+        if (!h->trace) return;
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        h->trace_ev.push_back(e);
+    };
+    for (cudaEvent_t e : h->trace_ev) cudaEventDestroy(e);
+    h->trace_ev.clear();
+    h->trace_ms.clear();
+    tr(h->s_in);
     for (int64_t w0 = 0; w0 < B; w0 += window) {
         const int64_t wn = std::min(window, B - w0);
         int slot = 0;
-        for (int64_t c0 = 0; c0 < wn; c0 += chunk, slot ^= 1) {
-            const int64_t cn = std::min(chunk, wn - c0);
+        int64_t cn = 0;
+        for (int64_t c0 = 0; c0 < wn; c0 += cn, slot ^= 1) {
+            const int64_t left = wn - c0;
+            // the last slice is cut in two: the kernel of its first half runs while the second half is copied
+            cn = std::min(chunk, left);
+            if (h->chunk == 0 && left <= chunk && left >= 8192) cn = (left * 3 / 4 + 31) / 32 * 32;
             const double *src = X + (size_t)(w0 + c0) * 3 * N;
             double *dst = (double *)h->dX.p + (size_t)c0 * 3 * N;
             if (!in_pinned) {
@@ -1027,7 +1061,9 @@ static int eval_host(cov_handle *h, const double *X, int64_t B, double *obj, int
                 free_armed[slot] = true;
             }
             CKD(cudaEventRecord(ev_in, h->s_in));
+            tr(h->s_in);
             CKD(cudaStreamWaitEvent(h->stream, ev_in, 0));
+            tr(h->stream);
             EvalOut out{};
             out.obj = (double *)h->d_obj.p + c0;
             out.count = count ? (long long *)h->d_count.p + c0 : nullptr;
@@ -1037,6 +1073,7 @@ static int eval_host(cov_handle *h, const double *X, int64_t B, double *obj, int
             rc = launch_on_main(h, dst, cn, out, true);
             if (rc != COV_OK) return done(rc);
             CKD(cudaEventRecord(ev_k, h->stream));
+            tr(h->stream);
             CKD(cudaStreamWaitEvent(h->s_out, ev_k, 0));
             const int64_t g0 = w0 + c0;
             CKD(cudaMemcpyAsync(obj_p ? (void *)(obj + g0) : (void *)(so + off_obj + (size_t)c0 * 8), out.obj,
@@ -1054,6 +1091,7 @@ static int eval_host(cov_handle *h, const double *X, int64_t B, double *obj, int
             if (progressive)
                 CKD(cudaMemcpyAsync(prg_p ? (void *)(progressive + g0) : (void *)(so + off_prg + (size_t)c0 * 8),
                                     out.progressive, (size_t)cn * 8, cudaMemcpyDeviceToHost, h->s_out));
+            tr(h->s_out);
         }
         // end of window: results home, device window reusable
         CKD(cudaStreamSynchronize(h->s_out));
@@ -1064,6 +1102,13 @@ static int eval_host(cov_handle *h, const double *X, int64_t B, double *obj, int
         if (!prg_p) memcpy(progressive + w0, so + off_prg, (size_t)wn * 8);
     }
 #undef CKD
+    if (h->trace && h->trace_ev.size() > 1) {
+        for (size_t k = 1; k < h->trace_ev.size(); ++k) {
+            float t = 0;
+            cudaEventElapsedTime(&t, h->trace_ev[0], h->trace_ev[k]);
+            h->trace_ms.push_back(t);
+        }
+    }
     return done(COV_OK);
 }
 
@@ -1223,6 +1268,14 @@ extern "C" int cov_memcpy_d2h(cov_handle *h, void *dst, const void *src, int64_t
     return COV_OK;
 }
 extern "C" int64_t cov_launch_count(const cov_handle *h) { return h ? h->launches : 0; }
+
+extern "C" int64_t cov_get_trace(const cov_handle *h, double *ms, int64_t cap)
+{
+    if (!h) return 0;
+    const int64_t n = (int64_t)h->trace_ms.size();
+    for (int64_t k = 0; k < n && k < cap && ms; ++k) ms[k] = h->trace_ms[k];
+    return n;
+}
 
 extern "C" int cov_last_kernel_ms(cov_handle *h, double *ms)
 {

@@ -396,8 +396,7 @@ cudaError_t launch_eval(const GridDesc &g, const ObjParams &o, const LaunchCfg &
                         cudaStream_t stream, LaunchInfo *info)
 {
     if (B <= 0) return cudaSuccess;
-    cudaError_t err = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
-    if (err != cudaSuccess) return err;
+    cudaError_t err = cudaSuccess; // `counter` is a fresh zeroed slot of the handle's counter ring
     const int N = o.N;
     LaunchInfo li{};
     if (cfg.kernel == COV_KERNEL_EXACT) {
@@ -451,7 +450,7 @@ cudaError_t launch_eval(const GridDesc &g, const ObjParams &o, const LaunchCfg &
         return cudaGetLastError();
     }
     // span kernels: the small-swarm variant when it applies, else one CTA per candidate
-    if (cfg.kernel != COV_KERNEL_SPAN_GENERAL && span_small_applies(g, N, cfg, nullptr, nullptr))
+    if (cfg.kernel != COV_KERNEL_SPAN_GENERAL && span_small_applies(g, N, cfg, B, nullptr, nullptr))
         return launch_span_small(g, o, cfg, dX, B, out, counter, stream, info);
     return launch_span_cta(g, o, cfg, dX, B, out, counter, stream, info);
 }

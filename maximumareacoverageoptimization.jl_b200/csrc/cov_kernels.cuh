@@ -20,14 +20,15 @@ struct LaunchInfo {
     int grid, block, smem_bytes, band_rows, planes_in_smem;
 };
 
-// Coverage objective over B candidates (device pointers). counter: one zeroed
-// unsigned long long per launch (work-chunk dispenser). Returns cudaError_t.
+// Coverage objective over B candidates (device pointers). counter: one ZEROED unsigned long long
+// per launch (work dispenser; the caller hands out fresh slots of a ring it zeroes in bulk, so no
+// memset sits between consecutive launches). Returns cudaError_t.
 cudaError_t launch_eval(const GridDesc &g, const ObjParams &o, const LaunchCfg &cfg, const double *dX,
                         long long B, const EvalOut &out, unsigned long long *counter,
                         cudaStream_t stream, LaunchInfo *info);
 
 // The small-swarm span kernel (cov_span_small.cu): N <= 8 and a framebuffer that fits shared memory.
-bool span_small_applies(const GridDesc &g, int N, const LaunchCfg &cfg, int *warps_out, int *chunk_out);
+bool span_small_applies(const GridDesc &g, int N, const LaunchCfg &cfg, long long B, int *warps_out, int *chunk_out);
 cudaError_t launch_span_small(const GridDesc &g, const ObjParams &o, const LaunchCfg &cfg, const double *dX,
                               long long B, const EvalOut &out, unsigned long long *counter, cudaStream_t stream,
                               LaunchInfo *info);

@@ -29,14 +29,25 @@
 namespace cov {
 
 constexpr int kSmallMaxN = 8;
+#ifndef COV_SMALL_ITEMS
+#define COV_SMALL_ITEMS 2
+#endif
+constexpr int kItems = COV_SMALL_ITEMS; // (disc, row) items in flight per lane
 
+// The framebuffer region doubles as the staging area of a unit's candidates during phase 1 (it is
+// all-zero between candidates and idle until phase 2), so it is at least chunk * 24 N bytes.
+__host__ __device__ inline int small_fb_bytes(const GridDesc &g, int N, int chunk)
+{
+    const int fb = round_up(g.ny * g.stride * 4, 16), stage = round_up(chunk * 3 * N * 8, 16);
+    return fb > stage ? fb : stage;
+}
 __host__ __device__ inline int small_warp_bytes(const GridDesc &g, int N, int chunk)
 {
-    const int fb = round_up(g.ny * g.stride * 4, 16);
     const int dp = chunk * N * 32;
     const int pre = chunk * 16; // 8 x u16 item prefixes per candidate
-    return fb + dp + pre;
+    return small_fb_bytes(g, N, chunk) + dp + pre;
 }
+__host__ __device__ inline int small_param_bytes(int N) { return round_up(5 * N * 8, 16); }
 
 template <bool MULTI, int CHUNK>
 __global__ void __launch_bounds__(512, 1)
@@ -50,17 +61,29 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
     const uint32_t lane = lane_id();
     const int N = o.N;
     const int planes_bytes = g.n_planes * g.plane_words * 4;
+    const int param_bytes = small_param_bytes(N);
     const int warp_bytes = small_warp_bytes(g, N, CHUNK);
-    const int fb_bytes = round_up(g.ny * g.stride * 4, 16);
+    const int fb_bytes = small_fb_bytes(g, N, CHUNK);
     uint32_t *planes_s = reinterpret_cast<uint32_t *>(smem_raw);
-    unsigned char *wbase = smem_raw + planes_bytes + (size_t)warp * warp_bytes;
+    double *par = reinterpret_cast<double *>(smem_raw + planes_bytes); // r_max, prev_x, prev_y, prev_z, cons3_G
+    unsigned char *wbase = smem_raw + planes_bytes + param_bytes + (size_t)warp * warp_bytes;
     uint32_t *fb = reinterpret_cast<uint32_t *>(wbase);
+    const double *stage = reinterpret_cast<const double *>(wbase);
     SDisc *dp = reinterpret_cast<SDisc *>(wbase + fb_bytes);
     uint4 *prefix = reinterpret_cast<uint4 *>(wbase + fb_bytes + CHUNK * N * 32);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + planes_bytes + (size_t)warps * warp_bytes);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + planes_bytes + param_bytes + (size_t)warps * warp_bytes);
 
-    stage_planes(g, planes_s, bar, planes_bytes); // TMA bulk copy of the fire planes, once per CTA
-    for (int t = lane; t < fb_bytes / 16; t += 32) reinterpret_cast<uint4 *>(fb)[t] = make_uint4(0, 0, 0, 0);
+    // the closure parameters once per CTA (with the shared-memory carve-out at its maximum there is next
+    // to no L1 left: every repeated global read would be an L2 round trip)
+    for (int t2 = threadIdx.x; t2 < N; t2 += blockDim.x) {
+        par[t2] = o.r_max[t2];
+        par[N + t2] = o.use_cons3 ? o.prev_x[t2] : 0.0;
+        par[2 * N + t2] = o.use_cons3 ? o.prev_y[t2] : 0.0;
+        par[3 * N + t2] = o.use_cons3 ? o.prev_z[t2] : 0.0;
+        par[4 * N + t2] = o.use_cons3 ? o.cons3_G[t2] : 0.0;
+    }
+    stage_planes(g, planes_s, bar, planes_bytes); // TMA bulk copy of the fire planes, once per CTA (syncs)
+    for (int t2 = lane; t2 < fb_bytes / 16; t2 += 32) reinterpret_cast<uint4 *>(fb)[t2] = make_uint4(0, 0, 0, 0);
     __syncwarp();
 
     const long long n_chunks = (B + CHUNK - 1) / CHUNK;
@@ -70,97 +93,106 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
     ictx.N = N;
     ictx.force_exact = force_exact;
 
+    // units are taken one ahead: while unit u is processed the candidates of unit u+1 are already on
+    // their way into L2
+    unsigned long long next = 0;
+    if (lane == 0) next = atomicAdd(counter, 1ull);
+    next = __shfl_sync(0xffffffffu, next, 0);
+    const bool x_aligned = (reinterpret_cast<unsigned long long>(X) & 15ull) == 0;
     for (;;) {
-        unsigned long long chunk = 0;
-        if (lane == 0) chunk = atomicAdd(counter, 1ull);
-        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        const unsigned long long chunk = next;
         if ((long long)chunk >= n_chunks) break;
+        if (lane == 0) next = atomicAdd(counter, 1ull);
+        next = __shfl_sync(0xffffffffu, next, 0);
         const long long base = (long long)chunk * CHUNK;
         const int in_chunk = (int)min((long long)CHUNK, B - base);
+        if ((long long)next < n_chunks) {
+            const char *nx_ptr = reinterpret_cast<const char *>(X + next * CHUNK * cstride);
+            const int nbytes = (int)min((long long)CHUNK, B - (long long)next * CHUNK) * cstride * 8;
+            for (int off = lane * 128; off < nbytes; off += 32 * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nx_ptr + off));
+        }
+        // stage the unit's candidates (contiguous in_chunk * 24 N bytes) in the framebuffer region
+        {
+            const int ndbl = in_chunk * cstride;
+            const double *src = X + base * cstride;
+            double *dst = reinterpret_cast<double *>(fb);
+            if (x_aligned && (ndbl & 1) == 0 && ((base * cstride) & 1) == 0) {
+                for (int t2 = lane; t2 < ndbl / 2; t2 += 32)
+                    reinterpret_cast<double2 *>(dst)[t2] = __ldg(reinterpret_cast<const double2 *>(src) + t2);
+            } else {
+                for (int t2 = lane; t2 < ndbl; t2 += 32) dst[t2] = __ldg(src + t2);
+            }
+        }
+        __syncwarp();
 
         // ---------------- phase 1: lane k sets up candidate k ----------------
         double my_viol = 0.0, my_prog = 0.0;
         int my_feas = 1;
         if ((int)lane < in_chunk) {
-            const double *xr = X + (base + lane) * cstride;
-            double px[kSmallMaxN], py[kSmallMaxN], pr[kSmallMaxN]; // compile-time indices only: registers
-#pragma unroll
-            for (int c = 0; c < kSmallMaxN; ++c) {
-                px[c] = py[c] = pr[c] = 0.0;
-                if (c < N) {
-                    px[c] = __ldg(xr + c);
-                    py[c] = __ldg(xr + N + c);
-                    pr[c] = __ldg(xr + 2 * N + c);
-                }
-            }
+            // Rolled loops over the discs (operands re-read through L1): phase 1 runs once per 32
+            // candidates, so compact code matters more here than a few extra loads.
+            const double *xr = stage + lane * cstride; // shared memory
+            const double *yr = xr + N, *rr = xr + 2 * N;
             // penalty: sequential FP64 sum in index order (src/TDM_STATIC_opt.jl:89-93)
-#pragma unroll
-            for (int i = 0; i < kSmallMaxN; ++i)
-                if (i < N) {
-                    const double diff = __dsub_rn(pr[i], o.r_max[i]);
-                    my_viol = __dadd_rn(my_viol, fabs(diff));
-                    if (out.progressive) my_prog = __dadd_rn(my_prog, julia_max0(diff));
-                }
+#pragma unroll 1
+            for (int i = 0; i < N; ++i) {
+                const double diff = __dsub_rn(rr[i], par[i]);
+                my_viol = __dadd_rn(my_viol, fabs(diff));
+                if (out.progressive) my_prog = __dadd_rn(my_prog, julia_max0(diff));
+            }
             bool bad = false;
             if (o.use_cons3) {
-#pragma unroll
-                for (int i = 0; i < kSmallMaxN; ++i)
-                    if (i < N) {
-                        const double ax = __dsub_rn(o.prev_x[i], px[i]);
-                        const double ay = __dsub_rn(o.prev_y[i], py[i]);
-                        const double az = __dsub_rn(o.prev_z[i], __ddiv_rn(pr[i], o.tan_half_fov));
-                        const double s =
-                            __dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az));
-                        bad |= (s >= o.cons3_G[i]);
-                    }
-            }
-            if (o.use_cons7) {
-#pragma unroll
-                for (int i = 0; i < kSmallMaxN; ++i)
-                    if (i < N) bad |= (py[i] < 200.0) && (pr[i] > o.cons7_R);
-            }
-            if (o.use_cons8) {
-#pragma unroll
-                for (int i = 0; i < kSmallMaxN; ++i)
-#pragma unroll
-                    for (int j2 = i + 1; j2 < kSmallMaxN; ++j2)
-                        if (j2 < N) {
-                            const double ax = __dsub_rn(px[i], px[j2]);
-                            const double ay = __dsub_rn(py[i], py[j2]);
-                            bad |= (__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)) < o.sep_T);
-                        }
-            }
-            my_feas = !bad;
-            // discs that may share cells with another disc of the candidate (bounding boxes, two cells
-            // of margin; NaN compares false -> "may share")
-            uint32_t shared_mask = 0;
-#pragma unroll
-            for (int a = 0; a < kSmallMaxN; ++a)
-#pragma unroll
-                for (int b2 = a + 1; b2 < kSmallMaxN; ++b2)
-                    if (b2 < N) {
-                        const double sr = pr[a] + pr[b2];
-                        const bool apart = (fabs(px[a] - px[b2]) >= sr + 2.0 * g.dx) ||
-                                           (fabs(py[a] - py[b2]) >= sr + 2.0 * g.dy);
-                        if (!apart) shared_mask |= (1u << a) | (1u << b2);
-                    }
-            uint32_t run = 0;
-            uint32_t pre[kSmallMaxN];
-#pragma unroll
-            for (int c = 0; c < kSmallMaxN; ++c) {
-                pre[c] = 0xffffu;
-                if (c < N) {
-                    SDisc d;
-                    const int rows = make_sdisc(g, px[c], py[c], pr[c], d);
-                    d.flags |= ((shared_mask >> c) & 1u) << 1;
-                    dp[lane * N + c] = d;
-                    run += (uint32_t)rows;
-                    pre[c] = run < 0xfffeu ? run : 0xfffeu; // inclusive prefix, saturated (see phase 2)
+#pragma unroll 1
+                for (int i = 0; i < N; ++i) {
+                    const double ax = __dsub_rn(par[N + i], xr[i]);
+                    const double ay = __dsub_rn(par[2 * N + i], yr[i]);
+                    const double az = __dsub_rn(par[3 * N + i], __ddiv_rn(rr[i], o.tan_half_fov));
+                    const double s = __dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az));
+                    bad |= (s >= par[4 * N + i]);
                 }
             }
-            prefix[lane] = make_uint4(pre[0] | (pre[1] << 16), pre[2] | (pre[3] << 16), pre[4] | (pre[5] << 16),
-                                      pre[6] | (pre[7] << 16));
+            if (o.use_cons7) {
+#pragma unroll 1
+                for (int i = 0; i < N; ++i) bad |= (yr[i] < 200.0) && (rr[i] > o.cons7_R);
+            }
+            // pairs: cons8 (src/TDM_Constraints.jl:157-172; unordered pairs decide the ordered loop) and the
+            // discs that may share cells with another disc of the candidate (bounding boxes, two cells of
+            // margin; NaN compares false -> "may share")
+            uint32_t shared_mask = 0;
+#pragma unroll 1
+            for (int a = 0; a < N - 1; ++a) {
+                const double xa = xr[a], ya = yr[a], ra = rr[a];
+#pragma unroll 1
+                for (int b2 = a + 1; b2 < N; ++b2) {
+                    const double ax = __dsub_rn(xa, xr[b2]), ay = __dsub_rn(ya, yr[b2]);
+                    if (o.use_cons8) bad |= (__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)) < o.sep_T);
+                    const double sr = ra + rr[b2];
+                    const bool apart = (fabs(ax) >= sr + 2.0 * g.dx) || (fabs(ay) >= sr + 2.0 * g.dy);
+                    if (!apart) shared_mask |= (1u << a) | (1u << b2);
+                }
+            }
+            my_feas = !bad;
+            uint32_t run = 0;
+            unsigned long long plo = ~0ull, phi = ~0ull; // 8 x u16 inclusive prefixes; unused slots 0xffff
+#pragma unroll 1
+            for (int c = 0; c < N; ++c) {
+                SDisc d;
+                const int rows = make_sdisc(g, xr[c], yr[c], rr[c], d);
+                d.flags |= ((shared_mask >> c) & 1u) << 1;
+                dp[lane * N + c] = d;
+                run += (uint32_t)rows;
+                const unsigned long long v = run < 0xfffeu ? run : 0xfffeu; // saturated (see phase 2)
+                const int sh = (c & 3) * 16;
+                if (c < 4) plo = (plo & ~(0xffffull << sh)) | (v << sh);
+                else phi = (phi & ~(0xffffull << sh)) | (v << sh);
+            }
+            prefix[lane] = make_uint4((uint32_t)plo, (uint32_t)(plo >> 32), (uint32_t)phi, (uint32_t)(phi >> 32));
         }
+        __syncwarp();
+        // the staging bytes go back to all-zero framebuffer
+        for (int t2 = lane; t2 < (in_chunk * cstride * 8 + 15) / 16; t2 += 32)
+            reinterpret_cast<uint4 *>(fb)[t2] = make_uint4(0, 0, 0, 0);
         __syncwarp();
 
         // ---------------- phase 2: one candidate at a time, (disc, row) items over the lanes ----------------
@@ -206,50 +238,49 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
                 for (int t = lane; t < fb_bytes / 16; t += 32)
                     reinterpret_cast<uint4 *>(fb)[t] = make_uint4(0, 0, 0, 0);
             } else {
-                // two items per lane and iteration: independent instruction streams hide the FP32 latencies
+                // kItems items per lane and iteration: independent instruction streams hide the FP32 and
+                // shared-memory latencies (the trip count is warp-uniform)
 #pragma unroll 1
-                for (uint32_t t0 = lane; t0 < total; t0 += 64) {
-                    const uint32_t t1 = t0 + 32;
-                    const bool has1 = t1 < total;
-                    // disc index = number of inclusive prefixes <= t (non-decreasing; unused slots 0xffff)
-                    int c0 = 0, c1 = 0;
-                    uint32_t before0 = 0u, before1 = 0u;
+                for (uint32_t tb = 0; tb < total; tb += 32 * kItems) {
+                    bool has[kItems];
+                    int c[kItems], j[kItems], lo[kItems], hi[kItems], st[kItems];
+                    SDisc d[kItems];
 #pragma unroll
-                    for (int q = 0; q < kSmallMaxN - 1; ++q) {
-                        if (t0 >= pre[q]) {
-                            c0 = q + 1;
-                            before0 = pre[q];
+                    for (int k = 0; k < kItems; ++k) {
+                        const uint32_t t = tb + 32 * k + lane;
+                        has[k] = t < total;
+                        const uint32_t tt = has[k] ? t : tb; // an idle slot shadows item tb, result discarded
+                        // disc index = number of inclusive prefixes <= t (non-decreasing; unused slots 0xffff)
+                        int cc = 0;
+                        uint32_t before = 0u;
+#pragma unroll
+                        for (int q = 0; q < kSmallMaxN - 1; ++q)
+                            if (tt >= pre[q]) {
+                                cc = q + 1;
+                                before = pre[q];
+                            }
+                        c[k] = cc;
+                        d[k] = cdp[cc];
+                        j[k] = (int)(d[k].rows & 0xffffu) + (int)(tt - before);
+                    }
+#pragma unroll
+                    for (int k = 0; k < kItems; ++k) {
+                        st[k] = fast_span(g, d[k], j[k], force_exact, lo[k], hi[k]);
+                        if (!has[k]) st[k] = kEmpty;
+                    }
+#pragma unroll
+                    for (int k = 0; k < kItems; ++k)
+                        if (st[k] == kSlow) {
+                            slow_item(g, ictx.xrow, N, c[k], j[k], (d[k].flags & 1u) || force_exact, lo[k], hi[k]);
+                            if (lo[k] <= hi[k]) st[k] = kSpan;
+                            else { st[k] = kEmpty; lo[k] = hi[k] = 1; }
                         }
-                        if (t1 >= pre[q]) {
-                            c1 = q + 1;
-                            before1 = pre[q];
-                        }
+#pragma unroll
+                    for (int k = 0; k < kItems; ++k) {
+                        const bool sh = (d[k].flags & 2u) != 0;
+                        any_shared |= sh && has[k];
+                        paint_span<MULTI>(g, fb, planes_s, j[k], lo[k], hi[k], st[k] == kSpan, sh, cnt);
                     }
-                    if (!has1) {
-                        c1 = c0;
-                        before1 = before0 + 32; // any valid row of the same disc: the result is discarded
-                    }
-                    const SDisc d0 = cdp[c0], d1 = cdp[c1];
-                    const int j0 = (int)(d0.rows & 0xffffu) + (int)(t0 - before0);
-                    const int j1 = (int)(d1.rows & 0xffffu) + (int)(t1 - before1);
-                    int lo0, hi0, lo1, hi1;
-                    int st0 = fast_span(g, d0, j0, force_exact, lo0, hi0);
-                    int st1 = fast_span(g, d1, j1, force_exact, lo1, hi1);
-                    if (!has1) st1 = kEmpty;
-                    if (st0 == kSlow) {
-                        slow_item(g, ictx.xrow, N, c0, j0, (d0.flags & 1u) || force_exact, lo0, hi0);
-                        if (lo0 <= hi0) st0 = kSpan;
-                        else { st0 = kEmpty; lo0 = hi0 = 1; }
-                    }
-                    if (st1 == kSlow) {
-                        slow_item(g, ictx.xrow, N, c1, j1, (d1.flags & 1u) || force_exact, lo1, hi1);
-                        if (lo1 <= hi1) st1 = kSpan;
-                        else { st1 = kEmpty; lo1 = hi1 = 1; }
-                    }
-                    const bool sh0 = (d0.flags & 2u) != 0, sh1 = (d1.flags & 2u) != 0;
-                    any_shared |= sh0 | (sh1 && has1);
-                    paint_span<MULTI>(g, fb, planes_s, j0, lo0, hi0, st0 == kSpan, sh0, cnt);
-                    paint_span<MULTI>(g, fb, planes_s, j1, lo1, hi1, st1 == kSpan, sh1, cnt);
                 }
                 // clear what the shared discs painted: every word of their bounding boxes
                 if (__any_sync(0xffffffffu, any_shared)) {
@@ -311,14 +342,19 @@ static cudaError_t set_smem_small(K kernel, int bytes)
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
-bool span_small_applies(const GridDesc &g, int N, const LaunchCfg &cfg, int *warps_out, int *chunk_out)
+// B: batch size (0: unknown / large).  A unit of work is CHUNK candidates processed by one warp, one
+// after the other, so a batch with fewer units than resident warps would leave the machine idle and
+// stretch the kernel to the latency of one unit: smaller batches take smaller chunks, and tiny ones
+// (a MADS poll set) go to the CTA-per-candidate kernel.
+bool span_small_applies(const GridDesc &g, int N, const LaunchCfg &cfg, long long B, int *warps_out, int *chunk_out)
 {
     if (N > kSmallMaxN || g.stride > 255 || g.ny > 65535) return false;
+    if (B > 0 && B < 128) return false;
     const int planes_bytes = g.n_planes * g.plane_words * 4;
     int best_w = 0, best_chunk = 0;
     for (int chunk : {32, 16}) {
         const int per = small_warp_bytes(g, N, chunk);
-        int w = (cfg.max_smem_optin - planes_bytes - 16) / per;
+        int w = (cfg.max_smem_optin - planes_bytes - small_param_bytes(N) - 16) / per;
         w = std::min(w, 16); // __launch_bounds__(512): 16 warps, <= 128 registers per thread
         if (cfg.warps_per_cta > 0) w = std::min(w, cfg.warps_per_cta);
         // prefer the 32-candidate chunk unless the 16-candidate one buys >= 25 % more warps
@@ -328,9 +364,43 @@ bool span_small_applies(const GridDesc &g, int N, const LaunchCfg &cfg, int *war
         }
     }
     if (best_w < 4) return false;
+    if (B > 0) {
+        // cost model (measured on B200): a unit costs ~2.65 us per candidate plus ~2.5 us of setup, and the
+        // kernel lasts as long as the busiest warp: pick the chunk that minimises ceil(units / warps) * unit
+        const double W = (double)best_w * cfg.num_sms;
+        double best_t = 0;
+        int pick = best_chunk;
+        for (int c = best_chunk; c >= 4; c /= 2) {
+            const double rounds = ceil((double)((B + c - 1) / c) / W);
+            const double tcost = rounds * (2.65 * c + 2.5);
+            if (c == best_chunk || tcost < best_t * 0.97) {
+                best_t = tcost;
+                pick = c;
+            }
+        }
+        best_chunk = pick;
+    }
     if (warps_out) *warps_out = best_w;
     if (chunk_out) *chunk_out = best_chunk;
     return true;
+}
+
+template <bool M, int C>
+static cudaError_t launch_small_variant(const GridDesc &g, const ObjParams &o, const LaunchCfg &cfg, const double *dX,
+                                        long long B, const EvalOut &out, unsigned long long *counter,
+                                        cudaStream_t stream, int grid, int warps, int smem)
+{
+    // the attribute is per function and per device: raise it only when it has to grow
+    static int configured_smem[64] = {0};
+    int dev = 0;
+    (void)cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || smem > configured_smem[dev]) {
+        cudaError_t err = cudaFuncSetAttribute(span_small_kernel<M, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (err != cudaSuccess) return err;
+        if (dev >= 0 && dev < 64) configured_smem[dev] = smem;
+    }
+    span_small_kernel<M, C><<<grid, warps * 32, smem, stream>>>(g, o, dX, B, out, counter, cfg.force_exact);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_span_small(const GridDesc &g, const ObjParams &o, const LaunchCfg &cfg, const double *dX,
@@ -338,9 +408,9 @@ cudaError_t launch_span_small(const GridDesc &g, const ObjParams &o, const Launc
                               LaunchInfo *info)
 {
     int warps = 0, chunk = 0;
-    if (!span_small_applies(g, o.N, cfg, &warps, &chunk)) return cudaErrorInvalidConfiguration;
+    if (!span_small_applies(g, o.N, cfg, B, &warps, &chunk)) return cudaErrorInvalidConfiguration;
     const bool multi = !(g.n_planes == 1 && g.n_classes == 1 && g.plane_mult[0] == 1);
-    const int smem = g.n_planes * g.plane_words * 4 + warps * small_warp_bytes(g, o.N, chunk) + 16;
+    const int smem = g.n_planes * g.plane_words * 4 + small_param_bytes(o.N) + warps * small_warp_bytes(g, o.N, chunk) + 16;
     const long long chunks = (B + chunk - 1) / chunk;
     const int grid = (int)std::min<long long>((chunks + warps - 1) / warps, (long long)cfg.num_sms);
     if (info) {
@@ -350,23 +420,25 @@ cudaError_t launch_span_small(const GridDesc &g, const ObjParams &o, const Launc
         info->band_rows = g.ny;
         info->planes_in_smem = 1;
     }
-    cudaError_t err;
-#define COV_LAUNCH_SMALL(M, C)                                                                             \
-    do {                                                                                                   \
-        err = set_smem_small(span_small_kernel<M, C>, smem);                                               \
-        if (err != cudaSuccess) return err;                                                                \
-        span_small_kernel<M, C><<<grid, warps * 32, smem, stream>>>(g, o, dX, B, out, counter,             \
-                                                                    cfg.force_exact);                      \
-    } while (0)
+#define COV_SMALL_CASE(M, C) \
+    case C: return launch_small_variant<M, C>(g, o, cfg, dX, B, out, counter, stream, grid, warps, smem)
     if (multi) {
-        if (chunk == 32) COV_LAUNCH_SMALL(true, 32);
-        else COV_LAUNCH_SMALL(true, 16);
+        switch (chunk) {
+            COV_SMALL_CASE(true, 32);
+            COV_SMALL_CASE(true, 16);
+            COV_SMALL_CASE(true, 8);
+            COV_SMALL_CASE(true, 4);
+        }
     } else {
-        if (chunk == 32) COV_LAUNCH_SMALL(false, 32);
-        else COV_LAUNCH_SMALL(false, 16);
+        switch (chunk) {
+            COV_SMALL_CASE(false, 32);
+            COV_SMALL_CASE(false, 16);
+            COV_SMALL_CASE(false, 8);
+            COV_SMALL_CASE(false, 4);
+        }
     }
-#undef COV_LAUNCH_SMALL
-    return cudaGetLastError();
+#undef COV_SMALL_CASE
+    return cudaErrorInvalidConfiguration;
 }
 
 } // namespace cov

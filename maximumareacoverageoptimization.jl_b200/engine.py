@@ -291,6 +291,13 @@ class CoverageEngine:
         self._check(lib.cov_last_kernel_ms(self._h, C.byref(v)))
         return v.value
 
+    def trace(self) -> np.ndarray:
+        """Timeline of the last host-path call under OPT_TRACE: (slices, 4) ms [h2d done, k start, k end, d2h done]."""
+        n = lib.cov_get_trace(self._h, None, 0)
+        out = np.zeros(n)
+        lib.cov_get_trace(self._h, out.ctypes.data_as(C.POINTER(C.c_double)), n)
+        return out.reshape(-1, 4)
+
     def kernel_time_total(self):
         """(summed coverage-kernel device time in ms, launches) since the engine was created."""
         ms, n = C.c_double(), C.c_int64()
