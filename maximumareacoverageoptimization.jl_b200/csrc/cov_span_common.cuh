@@ -35,11 +35,13 @@ __device__ __forceinline__ int make_sdisc(const GridDesc &g, double cx, double c
         if (isinf(R)) {
             r1 = g.ny;
         } else {
-            // rows j with |py_j - cy| < R, widened by one row and by the FP64 absorption error of
-            // fl(py - cy) for far-away centres
+            // rows j with |py_j - cy| < R, i.e. a < j < b with a = (cy-R)/dy + 1/2, b = (cy+R)/dy + 1/2:
+            // j from floor(a) + 1 to ceil(b) - 1, with a and b pushed outwards by `extra`, a bound on the
+            // FP64 rounding of this expression and of the reference's own fl(py - cy) for far-away
+            // centres, so that a row left out is certainly outside
             const double extra = (fabs(cy) + R) * 8.8817841970012523e-16 * g.inv_dy; // 2^-50
-            double lo = floor((cy - R) * g.inv_dy + 0.5 - extra);
-            double hi = ceil((cy + R) * g.inv_dy + 0.5 + extra);
+            double lo = floor((cy - R) * g.inv_dy + 0.5 - extra) + 1.0;
+            double hi = ceil((cy + R) * g.inv_dy + 0.5 + extra) - 1.0;
             if (!(lo <= (double)g.ny) || !(hi >= 1.0)) {
                 live = false;
             } else {
