@@ -181,12 +181,14 @@ __device__ __forceinline__ void count_word(const GridDesc &g, const uint32_t *pw
     }
 }
 
-// valid = false paints nothing (lets two items share one straight-line instruction stream).
 // fb_row0: the 1-based grid row held by framebuffer row 0 (banded framebuffers).
 // valid = false paints nothing (lets several items share one straight-line instruction stream).
 // The first word, the last word and (WIDE) one word in between are handled without branches; any
-// further whole words in a loop.
-template <bool MULTI, bool PLANES_SMEM = true, bool WIDE = false>
+// further whole words in a loop.  EARLY_PLANES (planes in global memory, single plane): the fire
+// words are requested BEFORE the framebuffer atomics, so the L2 round trip overlaps them; without it
+// a fire word is only read when the atomic left new bits, which is the better trade when the discs
+// overlap so heavily that most words are already covered (200 UAVs on 500 m x 500 m).
+template <bool MULTI, bool PLANES_SMEM = true, bool WIDE = false, bool EARLY_PLANES = false>
 __device__ __forceinline__ void paint_span(const GridDesc &g, uint32_t *fb, const uint32_t *planes, int j, int lo,
                                            int hi, bool valid, bool shared, uint32_t *cnt, int fb_row0 = 1)
 {
@@ -200,19 +202,42 @@ __device__ __forceinline__ void paint_span(const GridDesc &g, uint32_t *fb, cons
     const int wm = min(wa + 1, wb);
     uint32_t m2 = (WIDE && wb > wa + 1) ? 0xffffffffu : 0u;
     if (!valid) m0 = m1 = m2 = 0u;
+    constexpr bool EARLY = EARLY_PLANES && !MULTI && !PLANES_SMEM;
+    uint32_t p0 = 0, p1 = 0, p2 = 0;
+    if (EARLY) {
+        if (m0) p0 = __ldg(prow + wa);
+        if (m1) p1 = __ldg(prow + wb);
+        if (WIDE && m2) p2 = __ldg(prow + wm);
+    }
     if (shared) {
         if (m0) m0 &= ~atomicOr(frow + wa, m0);
         if (m1) m1 &= ~atomicOr(frow + wb, m1);
         if (WIDE && m2) m2 &= ~atomicOr(frow + wm, m2);
     }
-    count_word<MULTI, PLANES_SMEM>(g, prow + wa, m0, cnt);
-    count_word<MULTI, PLANES_SMEM>(g, prow + wb, m1, cnt);
-    if (WIDE) count_word<MULTI, PLANES_SMEM>(g, prow + wm, m2, cnt);
+    if (EARLY) {
+        cnt[0] += __popc(m0 & p0) + __popc(m1 & p1) + (WIDE ? __popc(m2 & p2) : 0);
+    } else {
+        count_word<MULTI, PLANES_SMEM>(g, prow + wa, m0, cnt);
+        count_word<MULTI, PLANES_SMEM>(g, prow + wb, m1, cnt);
+        if (WIDE) count_word<MULTI, PLANES_SMEM>(g, prow + wm, m2, cnt);
+    }
     if (valid) {
-        for (int w = wa + (WIDE ? 2 : 1); w < wb; ++w) { // whole words in between
-            uint32_t m = 0xffffffffu;
-            if (shared) m &= ~atomicOr(frow + w, m);
-            count_word<MULTI, PLANES_SMEM>(g, prow + w, m, cnt);
+        int w = wa + (WIDE ? 2 : 1);
+        if (EARLY) {
+            uint32_t pn = (w < wb) ? __ldg(prow + w) : 0u; // one word ahead of the atomics
+            for (; w < wb; ++w) {
+                const uint32_t pw = pn;
+                if (w + 1 < wb) pn = __ldg(prow + w + 1);
+                uint32_t m = 0xffffffffu;
+                if (shared) m &= ~atomicOr(frow + w, m);
+                cnt[0] += __popc(m & pw);
+            }
+        } else {
+            for (; w < wb; ++w) { // whole words in between
+                uint32_t m = 0xffffffffu;
+                if (shared) m &= ~atomicOr(frow + w, m);
+                count_word<MULTI, PLANES_SMEM>(g, prow + w, m, cnt);
+            }
         }
     }
 }

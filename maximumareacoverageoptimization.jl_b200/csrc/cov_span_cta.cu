@@ -64,7 +64,7 @@ static CtaPlan cta_plan(const GridDesc &g, int N, int smem_per_sm, int band_rows
     return p;
 }
 
-template <bool MULTI>
+template <bool MULTI, bool EARLY>
 __global__ void __launch_bounds__(kCtaThreads, kCtasPerSm)
 span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjParams o,
                 const double *__restrict__ X, long long B, EvalOut out, unsigned long long *counter,
@@ -227,8 +227,8 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
                         if (lo1 <= hi1) st1 = kSpan;
                         else { st1 = kEmpty; lo1 = hi1 = 1; }
                     }
-                    paint_span<MULTI, false, true>(g, fb, g.planes, jj0, lo0, hi0, st0 == kSpan, true, cnt, jb0);
-                    paint_span<MULTI, false, true>(g, fb, g.planes, jj1, lo1, hi1, st1 == kSpan, true, cnt, jb0);
+                    paint_span<MULTI, false, true, EARLY>(g, fb, g.planes, jj0, lo0, hi0, st0 == kSpan, true, cnt, jb0);
+                    paint_span<MULTI, false, true, EARLY>(g, fb, g.planes, jj1, lo1, hi1, st1 == kSpan, true, cnt, jb0);
                 }
             }
             __syncthreads();
@@ -289,18 +289,23 @@ cudaError_t launch_span_cta(const GridDesc &g, const ObjParams &o, const LaunchC
         info->band_rows = p.band_rows;
         info->planes_in_smem = 0;
     }
+    // moderate swarms: request the fire words ahead of the framebuffer atomics; dense swarms (their discs
+    // cover the domain more than once over): only read a fire word when the atomic left new bits
+    const bool early = !multi && o.N <= 96;
     cudaError_t err;
-    if (multi) {
-        err = cudaFuncSetAttribute(span_cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.total_bytes);
-        if (err != cudaSuccess) return err;
-        span_cta_kernel<true><<<grid, kCtaThreads, p.total_bytes, stream>>>(g, o, dX, B, out, counter, cfg.force_exact,
-                                                                             p.band_rows, p.fb_bytes);
-    } else {
-        err = cudaFuncSetAttribute(span_cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.total_bytes);
-        if (err != cudaSuccess) return err;
-        span_cta_kernel<false><<<grid, kCtaThreads, p.total_bytes, stream>>>(g, o, dX, B, out, counter, cfg.force_exact,
-                                                                              p.band_rows, p.fb_bytes);
-    }
+#define COV_LAUNCH_CTA(M, E)                                                                                      \
+    do {                                                                                                          \
+        err = cudaFuncSetAttribute(span_cta_kernel<M, E>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                                   p.total_bytes);                                                                \
+        if (err != cudaSuccess) return err;                                                                       \
+        span_cta_kernel<M, E><<<grid, kCtaThreads, p.total_bytes, stream>>>(g, o, dX, B, out, counter,            \
+                                                                            cfg.force_exact, p.band_rows,         \
+                                                                            p.fb_bytes);                          \
+    } while (0)
+    if (multi) COV_LAUNCH_CTA(true, false);
+    else if (early) COV_LAUNCH_CTA(false, true);
+    else COV_LAUNCH_CTA(false, false);
+#undef COV_LAUNCH_CTA
     return cudaGetLastError();
 }
 
