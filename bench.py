@@ -55,6 +55,16 @@ UNIT = "evals/s"
 WORKLOAD = "C2: 5 UAVs x 1M random candidates/step/GPU, 256x256 synthetic fire grid (BASELINE.json configs[1])"
 
 
+def load_traffic():
+    """DRAM bytes per launch of the bench kernel from the committed ncu capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if N_UAV == 5 and GRID_N == 256 and B_PER_GPU == 1_000_000 and os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d["dram_bytes_read"] + d["dram_bytes_write"]
+    return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -321,8 +331,8 @@ def main():
                        "penalties": "altitude penalty 1e5*sum|R - r_max|" + (f" + cons8 separation {SEP_MIN}" if SEP_MIN > 0 else "")},
             "tests_per_sec": value * tests_per_eval,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": f"of {peak_kind}",
-                         "bytes_per_eval": bytes_per_eval, "kernel": "span_small_kernel" if N <= 8 else "span_kernel", "kernel_ms": kernel_ms,
+                         "frac": achieved / hbm_peak, "traffic": load_traffic(), "peak_source": f"of {peak_kind}",
+                         "algorithmic_bytes_per_launch": B * bytes_per_eval, "bytes_per_eval": bytes_per_eval, "kernel": "span_small_kernel" if N <= 8 else "span_kernel", "kernel_ms": kernel_ms,
                          "note": "the kernel is instruction-issue bound, not HBM bound (DESIGN.md); see issue"},
             "issue": {"algorithmic_tests_per_sec_per_gpu": B * tests_per_eval / (kernel_ms * 1e-3),
                       "lane_instr_peak_per_sec": issue_peak,
