@@ -146,7 +146,8 @@ def cpu_port_rate(cov, bits, d, r_max, seconds: float, threads: int = 0, seed: i
     from oracle import c_oracle
     pts = cov.synth.points_from_bits(bits, GRID_N, d, d)
     nthr = c_oracle.num_threads() if threads <= 0 else threads
-    X = cov.synth.random_candidates(max(64, 16 * nthr), N_UAV, seed=seed)
+    X = cov.synth.random_candidates(max(2048, 128 * nthr), N_UAV, seed=seed)
+    c_oracle.eval_batch(X[:256], N_UAV, r_max, pts, sep_min=SEP_MIN, threads=threads)  # thread start-up, page-in
     t = time.perf_counter()
     c_oracle.eval_batch(X, N_UAV, r_max, pts, sep_min=SEP_MIN, threads=threads)
     rate = len(X) / (time.perf_counter() - t)
@@ -211,7 +212,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--cpu-seconds", type=float, default=24.0)
     args = ap.parse_args()
     global N_UAV, GRID_N, B_PER_GPU, WORKLOAD, SEP_MIN
     wl = WORKLOADS[args.workload]

@@ -11,6 +11,9 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 #include "cov_device.cuh"
@@ -18,6 +21,78 @@
 #include "../../include/coverage_cuda.h"
 
 using namespace cov;
+
+
+// ------------------------------------------------------------------------------------------
+// a few host threads for the staging copies of pageable buffers (a Julia Array is pageable: one
+// thread's memcpy into the pinned staging buffer would cap the host path at ~10 GB/s)
+// ------------------------------------------------------------------------------------------
+class CopyPool {
+public:
+    explicit CopyPool(int n)
+    {
+        for (int k = 0; k < n; ++k) workers_.emplace_back([this] { run(); });
+    }
+    ~CopyPool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : workers_) t.join();
+    }
+    // memcpy split over the pool and the calling thread; returns when all of it is done
+    void copy(void *dst, const void *src, size_t bytes)
+    {
+        const size_t parts = workers_.size() + 1;
+        if (bytes < (1u << 20) || parts == 1) {
+            memcpy(dst, src, bytes);
+            return;
+        }
+        const size_t per = ((bytes + parts - 1) / parts + 4095) / 4096 * 4096;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            for (size_t k = 1; k < parts; ++k) {
+                const size_t off = k * per;
+                if (off >= bytes) break;
+                const size_t n = std::min(per, bytes - off);
+                tasks_.push_back([=] { memcpy((char *)dst + off, (const char *)src + off, n); });
+                ++pending_;
+            }
+        }
+        cv_.notify_all();
+        memcpy(dst, src, std::min(per, bytes));
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+    }
+
+private:
+    void run()
+    {
+        for (;;) {
+            std::function<void()> job;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [this] { return stop_ || !tasks_.empty(); });
+                if (stop_ && tasks_.empty()) return;
+                job = std::move(tasks_.back());
+                tasks_.pop_back();
+            }
+            job();
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                if (--pending_ == 0) done_.notify_all();
+            }
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::vector<std::function<void()>> tasks_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    int pending_ = 0;
+    bool stop_ = false;
+};
 
 // ------------------------------------------------------------------------------------------
 // handle
@@ -61,6 +136,7 @@ struct cov_handle {
     void *h_out = nullptr;
     size_t h_out_cap = 0;
     void *h_small = nullptr; // pinned scratch: 4 KiB of scalars, then one candidate
+    void *h_poll = nullptr;  // pinned scratch of the small-batch path
 
     std::vector<cudaEvent_t> ev_pool; // recycled
     // (start, stop) events around every coverage-kernel launch since the last drain
@@ -72,6 +148,7 @@ struct cov_handle {
     int64_t launches = 0;
     LaunchInfo last_info{};
     int counter_next = 0; // next unused slot of the zeroed counter ring
+    CopyPool *pool = nullptr; // created on the first large pageable transfer
     // COV_OPT_TRACE: per-slice timeline of the last host-path call (ms since its first copy was queued)
     int trace = 0;
     std::vector<cudaEvent_t> trace_ev; // start, then per slice: h2d done, kernel start, kernel end, d2h done
@@ -297,6 +374,8 @@ extern "C" void cov_destroy(cov_handle *h)
         if (h->h_in[k]) cudaFreeHost(h->h_in[k]);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_small) cudaFreeHost(h->h_small);
+    if (h->h_poll) cudaFreeHost(h->h_poll);
+    delete h->pool;
     (void)drain_spans(h);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : h->trace_ev) cudaEventDestroy(e);
@@ -968,6 +1047,61 @@ extern "C" int cov_eval_batch_device(cov_handle *h, const double *dX, int64_t B,
 // The host pipeline: candidates are cut into slices; slice k's H2D copy (stream s_in), the kernel
 // of slice k-1 (main stream) and the D2H copy of slice k-2's results (stream s_out) overlap.
 // Pageable host buffers go through two pinned staging buffers; pinned ones are DMA'd in place.
+static void host_copy(cov_handle *h, void *dst, const void *src, size_t bytes)
+{
+    if (bytes >= (4u << 20)) {
+        if (!h->pool) {
+            const unsigned hc = std::thread::hardware_concurrency();
+            h->pool = new CopyPool((int)std::min(7u, std::max(2u, hc / 2) - 1u)); // + the calling thread
+        }
+        h->pool->copy(dst, src, bytes);
+    } else {
+        memcpy(dst, src, bytes);
+    }
+}
+
+// Small batches (a MADS poll set): one stream, pinned scratch, one synchronisation.
+static int eval_host_small(cov_handle *h, const double *X, int64_t B, double *obj, int64_t *count, uint8_t *feasible,
+                           int64_t *class_count, double *progressive)
+{
+    const int N = h->o.N;
+    const int ncls = h->g.n_classes;
+    const size_t in_bytes = (size_t)B * 3 * N * 8;
+    const size_t o_obj = 0, o_cnt = o_obj + (size_t)B * 8, o_cls = o_cnt + (count ? (size_t)B * 8 : 0),
+                 o_prg = o_cls + (class_count ? (size_t)B * 8 * ncls : 0), o_fea = o_prg + (progressive ? (size_t)B * 8 : 0),
+                 out_bytes = o_fea + (feasible ? (size_t)B : 0);
+    if (!h->h_poll) { // 2 MiB of pinned scratch: candidates at 0 (<= 256 KiB), results from 512 KiB on
+        cudaError_t e = cudaMallocHost(&h->h_poll, 2u << 20);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            h->h_poll = nullptr;
+            return fail(h, COV_ERR_NOMEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+        }
+    }
+    char *hin = (char *)h->h_poll, *hout = (char *)h->h_poll + (512u << 10);
+    OK(ensure(h, h->dX, std::max<size_t>(in_bytes, 1 << 20)));
+    OK(ensure(h, h->d_obj, std::max<size_t>(out_bytes, 1 << 20))); // one device block for every output
+    memcpy(hin, X, in_bytes);
+    CK(cudaMemcpyAsync(h->dX.p, hin, in_bytes, cudaMemcpyHostToDevice, h->stream));
+    char *dbase = (char *)h->d_obj.p;
+    EvalOut out{};
+    out.obj = (double *)(dbase + o_obj);
+    out.count = count ? (long long *)(dbase + o_cnt) : nullptr;
+    out.class_count = class_count ? (long long *)(dbase + o_cls) : nullptr;
+    out.progressive = progressive ? (double *)(dbase + o_prg) : nullptr;
+    out.feasible = feasible ? (unsigned char *)(dbase + o_fea) : nullptr;
+    OK(launch_on_main(h, (const double *)h->dX.p, B, out, true));
+    CK(cudaMemcpyAsync(hout, dbase, out_bytes, cudaMemcpyDeviceToHost, h->stream)); // ONE copy back
+    CK(cudaStreamSynchronize(h->stream));
+    const char *so = hout;
+    memcpy(obj, so + o_obj, (size_t)B * 8);
+    if (count) memcpy(count, so + o_cnt, (size_t)B * 8);
+    if (class_count) memcpy(class_count, so + o_cls, (size_t)B * 8 * ncls);
+    if (progressive) memcpy(progressive, so + o_prg, (size_t)B * 8);
+    if (feasible) memcpy(feasible, so + o_fea, (size_t)B);
+    return COV_OK;
+}
+
 static int eval_host(cov_handle *h, const double *X, int64_t B, double *obj, int64_t *count, uint8_t *feasible,
                      int64_t *class_count, double *progressive)
 {
@@ -978,6 +1112,8 @@ static int eval_host(cov_handle *h, const double *X, int64_t B, double *obj, int
     const int N = h->o.N;
     const int ncls = h->g.n_classes;
     const size_t row_bytes = (size_t)3 * N * 8;
+    if ((size_t)B * row_bytes <= (256u << 10) && (size_t)B * (25 + 8 * (size_t)ncls) <= (1536u << 10) && h->chunk == 0)
+        return eval_host_small(h, X, B, obj, count, feasible, class_count, progressive);
     // device window: at most ~1 GiB of candidates at a time
     const int64_t window = std::max<int64_t>(1, std::min<int64_t>(B, (int64_t)((1ull << 30) / row_bytes)));
     // slice size: ~16 MiB of candidates, a multiple of 32 candidates (keeps device slices 16-byte aligned)
@@ -1052,7 +1188,7 @@ static int eval_host(cov_handle *h, const double *X, int64_t B, double *obj, int
             double *dst = (double *)h->dX.p + (size_t)c0 * 3 * N;
             if (!in_pinned) {
                 if (free_armed[slot]) CKD(cudaEventSynchronize(ev_free[slot]));
-                memcpy(h->h_in[slot], src, (size_t)cn * row_bytes);
+                host_copy(h, h->h_in[slot], src, (size_t)cn * row_bytes);
                 src = (const double *)h->h_in[slot];
             }
             CKD(cudaMemcpyAsync(dst, src, (size_t)cn * row_bytes, cudaMemcpyHostToDevice, h->s_in));
@@ -1095,9 +1231,9 @@ static int eval_host(cov_handle *h, const double *X, int64_t B, double *obj, int
         }
         // end of window: results home, device window reusable
         CKD(cudaStreamSynchronize(h->s_out));
-        if (!obj_p) memcpy(obj + w0, so + off_obj, (size_t)wn * 8);
-        if (!cnt_p) memcpy(count + w0, so + off_cnt, (size_t)wn * 8);
-        if (!fea_p) memcpy(feasible + w0, so + off_fea, (size_t)wn);
+        if (!obj_p) host_copy(h, obj + w0, so + off_obj, (size_t)wn * 8);
+        if (!cnt_p) host_copy(h, count + w0, so + off_cnt, (size_t)wn * 8);
+        if (!fea_p) host_copy(h, feasible + w0, so + off_fea, (size_t)wn);
         if (!cls_p) memcpy(class_count + (size_t)w0 * ncls, so + off_cls, (size_t)wn * 8 * ncls);
         if (!prg_p) memcpy(progressive + w0, so + off_prg, (size_t)wn * 8);
     }

@@ -495,13 +495,19 @@ def test_host_pipeline_chunks_and_pinned(cov, orc, engine):
     assert np.array_equal(base["obj"][:300], sample["obj"])
 
 
-def test_multi_shards_on_one_device(cov, orc):
-    """cov_multi with two handles on device 0: contiguous shards, host gather."""
+@pytest.mark.parametrize("spread", [False, True])
+def test_multi_shards(cov, orc, spread):
+    """cov_multi: contiguous shards, host gather.  spread=False: two handles on device 0 (always runs);
+    spread=True: one handle per visible GPU (needs >= 2 devices, e.g. gpurun --gpus 2)."""
     import ctypes as C
     lib = cov._lib.lib
-    devs = (C.c_int * 2)(0, 0)
+    ndev = cov.device_count()
+    if spread and ndev < 2:
+        pytest.skip("needs at least two CUDA devices")
+    ids = list(range(ndev)) if spread else [0, 0]
+    devs = (C.c_int * len(ids))(*ids)
     m = C.c_void_p()
-    assert lib.cov_multi_create(devs, 2, C.byref(m)) == 0
+    assert lib.cov_multi_create(devs, len(ids), C.byref(m)) == 0
     try:
         N, B = 5, 3001
         r_max = np.full(N, 30 * T)
