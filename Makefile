@@ -18,6 +18,12 @@ $(LIB): $(SRCS) $(HDRS)
 $(ORACLE): oracle/coverage_oracle.c
 	$(GCC) -O2 -fPIC -shared -pthread -ffp-contract=off -fno-fast-math -fvisibility=hidden -o $@ $< -lm
 
+# checking variant: device asserts on every framebuffer / plane index (compute-sanitizer is closed on the pool)
+debug-bounds:
+	mkdir -p build/variants
+	$(NVCC) $(filter-out -Xptxas -v,$(NVCCFLAGS)) -DCOV_DEBUG_BOUNDS -shared -o build/variants/lib_debug_bounds.so $(SRCS) -cudart static
+	@echo 'run: COVERAGE_CUDA_LIB=$$PWD/build/variants/lib_debug_bounds.so python -m pytest tests -m gpu'
+
 clean:
 	rm -f $(LIB) $(ORACLE)
-.PHONY: all clean
+.PHONY: all clean debug-bounds

@@ -7,6 +7,15 @@
 #include "cov_device.cuh"
 #include "cov_kernel_common.cuh"
 
+// -DCOV_DEBUG_BOUNDS builds a checking variant of the library (device asserts on every framebuffer / plane
+// index): the in-house substitute for compute-sanitizer, which is closed on the GPU pool.
+#ifdef COV_DEBUG_BOUNDS
+#include <cassert>
+#define COV_ASSERT(c) assert(c)
+#else
+#define COV_ASSERT(c) ((void)0)
+#endif
+
 namespace cov {
 
 struct __align__(16) SDisc {
@@ -196,6 +205,8 @@ __device__ __forceinline__ void paint_span(const GridDesc &g, uint32_t *fb, cons
     const int wa = a >> 5, wb = b >> 5;
     uint32_t *frow = fb + (j - fb_row0) * g.stride;
     const uint32_t *prow = planes + (size_t)(j - 1) * g.stride;
+    COV_ASSERT(!valid || (lo >= 1 && lo <= hi && hi <= g.nx && j >= fb_row0 && j <= g.ny));
+    COV_ASSERT(wa >= 0 && wa < g.wpr && wb >= 0 && wb < g.wpr);
     const uint32_t ma = 0xffffffffu << (a & 31), mb = 0xffffffffu >> (31 - (b & 31));
     uint32_t m0 = (wa == wb) ? (ma & mb) : ma;
     uint32_t m1 = (wa == wb) ? 0u : mb;

@@ -206,12 +206,14 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
                     const int c0 = lo;
                     int c1 = c0;
                     while (c1 + 1 < N && prefix[c1 + 1] <= u1) ++c1;
+                    COV_ASSERT(c0 >= 0 && c0 < N && c1 >= 0 && c1 < N);
                     const SDisc d0 = dp[c0], d1 = dp[c1];
                     const int j0 = max((int)(d0.rows & 0xffffu), jb0) + (int)((u0 - prefix[c0]) << 5) + lane;
                     const int j1 = max((int)(d1.rows & 0xffffu), jb0) + (int)((u1 - prefix[c1]) << 5) + lane;
                     const bool in0 = j0 <= min((int)(d0.rows >> 16), jb1);
                     const bool in1 = has1 && j1 <= min((int)(d1.rows >> 16), jb1);
                     const int jj0 = in0 ? j0 : jb0, jj1 = in1 ? j1 : jb0; // any row of the band: result discarded
+                    COV_ASSERT(jj0 >= jb0 && jj0 <= jb1 && jj1 >= jb0 && jj1 <= jb1);
                     int lo0, hi0, lo1, hi1;
                     int st0 = fast_span(g, d0, jj0, force_exact, lo0, hi0);
                     int st1 = fast_span(g, d1, jj1, force_exact, lo1, hi1);

@@ -259,9 +259,11 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
                                 cc = q + 1;
                                 before = pre[q];
                             }
+                        COV_ASSERT(cc < N);
                         c[k] = cc;
                         d[k] = cdp[cc];
                         j[k] = (int)(d[k].rows & 0xffffu) + (int)(tt - before);
+                        COV_ASSERT(j[k] >= 1 && j[k] <= (int)(d[k].rows >> 16) && j[k] <= g.ny);
                     }
 #pragma unroll
                     for (int k = 0; k < kItems; ++k) {
