@@ -134,6 +134,32 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(local: int):
+    """Pin this rank to the CPUs next to its GPU before any pinned host memory is allocated (first touch
+    then places the staging pages on the GPU's NUMA node). Best effort: returns a note for the JSON line."""
+    try:
+        import torch
+        prop = torch.cuda.get_device_properties(local)
+        bus = f"{getattr(prop, 'pci_domain_id', 0):04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+            return f"bound to {len(use)} CPUs local to {bus}"
+        return f"no narrower local CPU set for {bus} ({len(allowed)} CPUs allowed)"
+    except Exception as e:  # noqa: BLE001  (sysfs layout, permissions, torch version)
+        return f"not bound ({type(e).__name__})"
+
+
 def make_workload(cov):
     d = 500.0 / GRID_N
     bits, n_fire = cov.synth.fire_grid(GRID_N, dense=(GRID_N == 100))
@@ -233,6 +259,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libcoverage_cuda has no CPU fallback")
     torch.cuda.set_device(local)
+    numa_note = bind_to_gpu_numa_node(local) if world > 1 else "single rank: not bound"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B = args.batch
@@ -342,6 +369,7 @@ def main():
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * row_bytes, "d2h_bytes_per_step": B * 17,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
+            "host_placement": numa_note,
             "clocks": clocks,
             "check": {"count_sum_last_step": int(cnt.sum()), "obj_finite": bool(np.isfinite(obj).all())},
         }
