@@ -133,7 +133,10 @@ __device__ __forceinline__ int fast_span(const GridDesc &g, const SDisc &d, int 
     const float dy2 = y * y;
     const float thi = d.Tf + d.delta, tlo = d.Tf - d.delta;
     const float w2 = d.Tf - dy2;
-    const float w = w2 > 0.0f ? w2 * rsqrtf(w2) : 0.0f; // an estimate only: the ends are certified below
+    // an estimate only (one MUFU, flush-to-zero): whatever it returns, the ends are certified below
+    float rs;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(w2));
+    const float w = w2 > 0.0f ? w2 * rs : 0.0f;
     const float ulo = ceilf((d.fx - w) * g.inv_dxf);
     const float uhi = floorf((d.fx + w) * g.inv_dxf);
     // estimate says "no cell" (a chord shorter than the cell pitch): probe the cell left of the centre
@@ -153,10 +156,10 @@ __device__ __forceinline__ int fast_span(const GridDesc &g, const SDisc &d, int 
     lo = (int)fminf(lof, nxf);
     hi = (int)fmaxf(hif, 1.0f);
     const bool irregular = (d.flags & 1u) || force_exact;
-    if (irregular) return kSlow;
-    if (dy2 > thi) return kEmpty; // the whole row is certainly outside
-    if (est_empty) return ok_empty ? kEmpty : kSlow;
-    return ok_span ? kSpan : kSlow;
+    // branch-free status: irregular -> slow; row certainly outside -> empty; else by the certificates
+    int st = est_empty ? (ok_empty ? kEmpty : kSlow) : (ok_span ? kSpan : kSlow);
+    st = (dy2 > thi) ? kEmpty : st;
+    return irregular ? kSlow : st;
 }
 
 // The slow path of an item: FP64 exact walk from the guesses.

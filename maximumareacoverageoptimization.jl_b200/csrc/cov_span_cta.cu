@@ -220,14 +220,20 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
                     if (!in0) st0 = kEmpty;
                     if (!in1) st1 = kEmpty;
                     if (st0 == kSlow) {
-                        slow_item(g, xr, N, c0, jj0, (d0.flags & 1u) || force_exact, lo0, hi0);
-                        if (lo0 <= hi0) st0 = kSpan;
-                        else { st0 = kEmpty; lo0 = hi0 = 1; }
+                        int l2 = lo0, h2 = hi0; // temporaries: lo/hi stay in registers
+                        slow_item(g, xr, N, c0, jj0, (d0.flags & 1u) || force_exact, l2, h2);
+                        if (l2 <= h2) st0 = kSpan;
+                        else { st0 = kEmpty; l2 = h2 = 1; }
+                        lo0 = l2;
+                        hi0 = h2;
                     }
                     if (st1 == kSlow) {
-                        slow_item(g, xr, N, c1, jj1, (d1.flags & 1u) || force_exact, lo1, hi1);
-                        if (lo1 <= hi1) st1 = kSpan;
-                        else { st1 = kEmpty; lo1 = hi1 = 1; }
+                        int l2 = lo1, h2 = hi1; // temporaries: lo/hi stay in registers
+                        slow_item(g, xr, N, c1, jj1, (d1.flags & 1u) || force_exact, l2, h2);
+                        if (l2 <= h2) st1 = kSpan;
+                        else { st1 = kEmpty; l2 = h2 = 1; }
+                        lo1 = l2;
+                        hi1 = h2;
                     }
                     paint_span<MULTI, false, true, EARLY>(g, fb, g.planes, jj0, lo0, hi0, st0 == kSpan, true, cnt, jb0);
                     paint_span<MULTI, false, true, EARLY>(g, fb, g.planes, jj1, lo1, hi1, st1 == kSpan, true, cnt, jb0);

@@ -273,9 +273,12 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
 #pragma unroll
                     for (int k = 0; k < kItems; ++k)
                         if (st[k] == kSlow) {
-                            slow_item(g, ictx.xrow, N, c[k], j[k], (d[k].flags & 1u) || force_exact, lo[k], hi[k]);
-                            if (lo[k] <= hi[k]) st[k] = kSpan;
-                            else { st[k] = kEmpty; lo[k] = hi[k] = 1; }
+                            int l2 = lo[k], h2 = hi[k]; // temporaries: the arrays stay in registers
+                            slow_item(g, ictx.xrow, N, c[k], j[k], (d[k].flags & 1u) || force_exact, l2, h2);
+                            if (l2 <= h2) st[k] = kSpan;
+                            else { st[k] = kEmpty; l2 = h2 = 1; }
+                            lo[k] = l2;
+                            hi[k] = h2;
                         }
 #pragma unroll
                     for (int k = 0; k < kItems; ++k) {
