@@ -180,13 +180,19 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
                 SDisc d;
                 const int rows = make_sdisc(g, xr[c], yr[c], rr[c], d);
                 d.flags |= ((shared_mask >> c) & 1u) << 1;
+                // bits 16..31: (first row) - (items before this disc) + 32768, so that item t is row base + t
+                d.flags |= (uint32_t)((int)(d.rows & 0xffffu) - (int)run + 32768) << 16;
                 dp[lane * N + c] = d;
                 run += (uint32_t)rows;
-                const unsigned long long v = run < 0xfffeu ? run : 0xfffeu; // saturated (see phase 2)
+                const unsigned long long v = run; // ny <= 4095 and N <= 8 keep it below 0x8000
                 const int sh = (c & 3) * 16;
                 if (c < 4) plo = (plo & ~(0xffffull << sh)) | (v << sh);
                 else phi = (phi & ~(0xffffull << sh)) | (v << sh);
             }
+            // slot 7 is never compared against (a disc index needs N - 1 <= 7 prefixes): it carries the total
+            // (N == 8: slot 7 is the last inclusive prefix, which is the total as well); bit 15 of the slot,
+            // free because totals stay below 0x8000: some disc of the candidate goes through the framebuffer
+            phi = (phi & 0x0000ffffffffffffull) | ((unsigned long long)(run | (shared_mask ? 0x8000u : 0u)) << 48);
             prefix[lane] = make_uint4((uint32_t)plo, (uint32_t)(plo >> 32), (uint32_t)phi, (uint32_t)(phi >> 32));
         }
         __syncwarp();
@@ -205,64 +211,41 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
             const uint4 pq = prefix[kc];
             uint32_t pre[kSmallMaxN] = {pq.x & 0xffffu, pq.x >> 16, pq.y & 0xffffu, pq.y >> 16,
                                         pq.z & 0xffffu, pq.z >> 16, pq.w & 0xffffu, pq.w >> 16};
-            // total number of items = the last real prefix
-            uint32_t total = 0;
-#pragma unroll
-            for (int c = 0; c < kSmallMaxN; ++c)
-                if (c < N) total = pre[c];
+            const uint32_t total = pre[kSmallMaxN - 1] & 0x7fffu; // number of items (slot 7, see phase 1)
+            const bool any_shared = (pre[kSmallMaxN - 1] & 0x8000u) != 0;
             const SDisc *cdp = dp + kc * N;
             ictx.xrow = X + (base + kc) * cstride;
             uint32_t cnt[MULTI ? kMaxClasses : 1];
 #pragma unroll
             for (int k = 0; k < (MULTI ? kMaxClasses : 1); ++k) cnt[k] = 0;
 
-            bool any_shared = false;
-            if (total >= 0xfffeu) {
-                // >= 65534 (disc, row) items cannot happen on a framebuffer that fits shared memory, but
-                // stay safe: disc by disc, everything through the framebuffer
-                for (int c = 0; c < N; ++c) {
-                    const SDisc d = cdp[c];
-                    const int r0 = d.rows & 0xffffu, r1 = d.rows >> 16;
-                    for (int j = r0 + (int)lane; j <= r1; j += 32) {
-                        int lo, hi;
-                        int st = fast_span(g, d, j, force_exact, lo, hi);
-                        if (st == kSlow) {
-                            slow_item(g, ictx.xrow, N, c, j, (d.flags & 1u) || force_exact, lo, hi);
-                            if (lo <= hi) st = kSpan;
-                            else { st = kEmpty; lo = hi = 1; }
-                        }
-                        paint_span<MULTI>(g, fb, planes_s, j, lo, hi, st == kSpan, true, cnt);
-                    }
-                }
-                __syncwarp();
-                for (int t = lane; t < fb_bytes / 16; t += 32)
-                    reinterpret_cast<uint4 *>(fb)[t] = make_uint4(0, 0, 0, 0);
-            } else {
+            {
                 // kItems items per lane and iteration: independent instruction streams hide the FP32 and
                 // shared-memory latencies (the trip count is warp-uniform)
 #pragma unroll 1
                 for (uint32_t tb = 0; tb < total; tb += 32 * kItems) {
                     bool has[kItems];
                     int c[kItems], j[kItems], lo[kItems], hi[kItems], st[kItems];
+                    uint32_t tt[kItems];
                     SDisc d[kItems];
 #pragma unroll
                     for (int k = 0; k < kItems; ++k) {
                         const uint32_t t = tb + 32 * k + lane;
                         has[k] = t < total;
-                        const uint32_t tt = has[k] ? t : tb; // an idle slot shadows item tb, result discarded
-                        // disc index = number of inclusive prefixes <= t (non-decreasing; unused slots 0xffff)
-                        int cc = 0;
-                        uint32_t before = 0u;
+                        tt[k] = has[k] ? t : tb; // an idle slot shadows item tb, result discarded
+                        c[k] = 0;
+                    }
+                    // disc index = number of inclusive prefixes <= t (non-decreasing; unused slots 0xffff).
+                    // (A warp-uniform switch on N into a fall-through chain of N - 1 compares measured slower.)
 #pragma unroll
-                        for (int q = 0; q < kSmallMaxN - 1; ++q)
-                            if (tt >= pre[q]) {
-                                cc = q + 1;
-                                before = pre[q];
-                            }
-                        COV_ASSERT(cc < N);
-                        c[k] = cc;
-                        d[k] = cdp[cc];
-                        j[k] = (int)(d[k].rows & 0xffffu) + (int)(tt - before);
+                    for (int q = 0; q < kSmallMaxN - 1; ++q)
+#pragma unroll
+                        for (int k = 0; k < kItems; ++k) c[k] += (tt[k] >= pre[q]) ? 1 : 0;
+#pragma unroll
+                    for (int k = 0; k < kItems; ++k) {
+                        COV_ASSERT(c[k] < N);
+                        d[k] = cdp[c[k]];
+                        j[k] = (int)(d[k].flags >> 16) - 32768 + (int)tt[k];
                         COV_ASSERT(j[k] >= 1 && j[k] <= (int)(d[k].rows >> 16) && j[k] <= g.ny);
                     }
 #pragma unroll
@@ -283,12 +266,11 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
 #pragma unroll
                     for (int k = 0; k < kItems; ++k) {
                         const bool sh = (d[k].flags & 2u) != 0;
-                        any_shared |= sh && has[k];
                         paint_span<MULTI>(g, fb, planes_s, j[k], lo[k], hi[k], st[k] == kSpan, sh, cnt);
                     }
                 }
                 // clear what the shared discs painted: every word of their bounding boxes
-                if (__any_sync(0xffffffffu, any_shared)) {
+                if (any_shared) { // warp-uniform
                     __syncwarp();
 #pragma unroll 1
                     for (int c = 0; c < N; ++c) {
@@ -353,7 +335,7 @@ static cudaError_t set_smem_small(K kernel, int bytes)
 // (a MADS poll set) go to the CTA-per-candidate kernel.
 bool span_small_applies(const GridDesc &g, int N, const LaunchCfg &cfg, long long B, int *warps_out, int *chunk_out)
 {
-    if (N > kSmallMaxN || g.stride > 255 || g.ny > 65535) return false;
+    if (N > kSmallMaxN || g.stride > 255 || g.ny > 4095) return false; // 8 x ny items fit 15 bits (row base in 16)
     if (B > 0 && B < 128) return false;
     const int planes_bytes = g.n_planes * g.plane_words * 4;
     int best_w = 0, best_chunk = 0;
