@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdint>
+#include <type_traits>
 #include "cov_device.cuh"
 #include "cov_kernel_common.cuh"
 #include "cov_span_common.cuh"
@@ -29,10 +30,6 @@
 namespace cov {
 
 constexpr int kSmallMaxN = 8;
-#ifndef COV_SMALL_ITEMS
-#define COV_SMALL_ITEMS 2
-#endif
-constexpr int kItems = COV_SMALL_ITEMS; // (disc, row) items in flight per lane
 
 // The framebuffer region doubles as the staging area of a unit's candidates during phase 1 (it is
 // all-zero between candidates and idle until phase 2), so it is at least chunk * 24 N bytes.
@@ -220,10 +217,10 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
             for (int k = 0; k < (MULTI ? kMaxClasses : 1); ++k) cnt[k] = 0;
 
             {
-                // kItems items per lane and iteration: independent instruction streams hide the FP32 and
-                // shared-memory latencies (the trip count is warp-uniform)
-#pragma unroll 1
-                for (uint32_t tb = 0; tb < total; tb += 32 * kItems) {
+                // K items per lane in one pass over 32 K consecutive items: independent instruction streams hide
+                // the FP32 and shared-memory latencies
+                auto pass = [&](auto K_, const uint32_t tb) {
+                    constexpr int kItems = decltype(K_)::value;
                     bool has[kItems];
                     int c[kItems], j[kItems], lo[kItems], hi[kItems], st[kItems];
                     uint32_t tt[kItems];
@@ -267,6 +264,18 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
                     for (int k = 0; k < kItems; ++k) {
                         const bool sh = (d[k].flags & 2u) != 0;
                         paint_span<MULTI>(g, fb, planes_s, j[k], lo[k], hi[k], st[k] == kSpan, sh, cnt);
+                    }
+                };
+                // two items per lane while more than 32 remain, one for the last short stretch (the trip
+                // count is warp-uniform)
+#pragma unroll 1
+                for (uint32_t tb = 0; tb < total;) {
+                    if (total - tb > 32u) {
+                        pass(std::integral_constant<int, 2>{}, tb);
+                        tb += 64;
+                    } else {
+                        pass(std::integral_constant<int, 1>{}, tb);
+                        tb += 32;
                     }
                 }
                 // clear what the shared discs painted: every word of their bounding boxes
