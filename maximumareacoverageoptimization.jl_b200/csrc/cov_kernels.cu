@@ -171,7 +171,7 @@ template <bool MULTI, bool PLANES_SMEM>
 __global__ void __launch_bounds__(256)
 brute_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjParams o,
              const double *__restrict__ X, long long B, EvalOut out, unsigned long long *counter,
-             int force_exact)
+             int force_exact, int unit)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warps = blockDim.x >> 5;
@@ -190,15 +190,17 @@ brute_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjPara
     if (PLANES_SMEM) stage_planes(g, planes_s, bar, planes_bytes);
     const uint32_t *planes = PLANES_SMEM ? planes_s : g.planes;
 
-    const long long n_chunks = (B + 31) / 32;
+    // unit = candidates a warp takes per grab: 32 (coalesced result stores) for big batches, 1 when the batch
+    // would otherwise leave warps idle (one candidate is already ~10^5 tests)
+    const long long n_chunks = (B + unit - 1) / unit;
     const int cstride = 3 * N;
     for (;;) {
         unsigned long long chunk = 0;
         if (lane == 0) chunk = atomicAdd(counter, 1ull);
         chunk = __shfl_sync(0xffffffffu, chunk, 0);
         if ((long long)chunk >= n_chunks) break;
-        const long long base = (long long)chunk * 32;
-        const int in_chunk = (int)min(32ll, B - base);
+        const long long base = (long long)chunk * unit;
+        const int in_chunk = (int)min((long long)unit, B - base);
         double my_obj = 0.0, my_prog = 0.0;
         long long my_cnt = 0;
         long long my_cls[kMaxClasses];
@@ -423,9 +425,10 @@ cudaError_t launch_eval(const GridDesc &g, const ObjParams &o, const LaunchCfg &
         if (warps * per_warp + 16 > cfg.max_smem_optin) return cudaErrorInvalidConfiguration;
         const bool planes_smem = planes_bytes + warps * per_warp + 16 <= cfg.max_smem_optin;
         const int smem = (planes_smem ? planes_bytes : 0) + warps * per_warp + 16;
-        const long long chunks = (B + 31) / 32;
-        const long long want = (chunks + warps - 1) / warps;
         const int per_sm = max(1, min(8, cfg.max_smem_optin / max(smem, 1)));
+        const int unit = (B / 32 >= 4ll * cfg.num_sms * per_sm * warps) ? 32 : 1;
+        const long long chunks = (B + unit - 1) / unit;
+        const long long want = (chunks + warps - 1) / warps;
         const int grid = (int)std::min<long long>(want, (long long)cfg.num_sms * per_sm);
         li.grid = grid;
         li.block = warps * 32;
@@ -437,7 +440,7 @@ cudaError_t launch_eval(const GridDesc &g, const ObjParams &o, const LaunchCfg &
         err = set_smem(brute_kernel<M, S>, smem);                                                   \
         if (err != cudaSuccess) return err;                                                         \
         brute_kernel<M, S><<<grid, warps * 32, smem, stream>>>(g, o, dX, B, out, counter,           \
-                                                               cfg.force_exact);                    \
+                                                               cfg.force_exact, unit);              \
     } while (0)
         if (multi) {
             if (planes_smem) COV_LAUNCH_BRUTE(true, true);
