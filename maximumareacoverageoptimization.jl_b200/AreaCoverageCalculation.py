@@ -210,3 +210,19 @@ def rmvCoveredPOI(circles, points):
     r.points.keep(~covered)
     r.mark_synced()
     return r.points
+
+
+_union_engine = None
+
+
+def unionArea(circles, engine: CoverageEngine | None = None) -> float:
+    """Continuous variant: exact area of the union of the discs [x;y;R], by boundary
+    integration on the device (cov_union_area_batch).  The reference ships only the pair primitives of
+    this method (src/Base_Functions.jl:230-355) and no driver."""
+    global _union_engine
+    circles = np.ascontiguousarray(circles, dtype=np.float64).ravel()
+    if engine is None:
+        if _union_engine is None:
+            _union_engine = CoverageEngine(0)
+        engine = _union_engine
+    return float(engine.union_area(circles.reshape(1, -1), circles.size // 3)[0])

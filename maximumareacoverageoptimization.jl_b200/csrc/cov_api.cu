@@ -1330,6 +1330,31 @@ extern "C" int cov_argmin(cov_handle *h, const double *X, int64_t B, int32_t bar
     return COV_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// continuous variant: exact union area of the discs (no grid involved)
+// ------------------------------------------------------------------------------------------
+extern "C" int cov_union_area_batch(cov_handle *h, const double *X, int64_t B, int64_t N, double *area)
+{
+    if (!h) return fail(nullptr, COV_ERR_INVALID, "NULL handle");
+    DeviceGuard dg(h->device);
+    if (N < 1 || N > 64) return fail(h, COV_ERR_LIMIT, "cov_union_area_batch: N must be 1..64");
+    if (B < 0 || (B > 0 && (!X || !area))) return fail(h, COV_ERR_INVALID, "cov_union_area_batch: bad arguments");
+    const size_t row_bytes = (size_t)3 * N * 8;
+    const int64_t window = std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(B, 1), (int64_t)((256ull << 20) / row_bytes)));
+    OK(ensure(h, h->dX, (size_t)window * row_bytes));
+    OK(ensure(h, h->d_obj, (size_t)window * 8));
+    for (int64_t w0 = 0; w0 < B; w0 += window) {
+        const int64_t wn = std::min(window, B - w0);
+        CK(cudaMemcpyAsync(h->dX.p, X + (size_t)w0 * 3 * N, (size_t)wn * row_bytes, cudaMemcpyHostToDevice, h->stream));
+        CK(launch_union_area((const double *)h->dX.p, (long long)wn, (int)N, (double *)h->d_obj.p, h->stream));
+        h->launches += 1;
+        CK(cudaMemcpyAsync(area + w0, h->d_obj.p, (size_t)wn * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return COV_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // streams, memory, timing
 // ------------------------------------------------------------------------------------------

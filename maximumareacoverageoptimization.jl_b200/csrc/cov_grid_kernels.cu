@@ -485,6 +485,94 @@ cudaError_t launch_generate(double *dX, long long B, int N, unsigned long long s
     return cudaGetLastError();
 }
 
+
+// ---- continuous variant: exact area of the union of the discs of a candidate ----
+// Boundary integration (Green's theorem): for every circle, the arcs that lie inside no other disc
+// contribute 1/2 * integral (x dy - y dx) = 1/2 [R^2 (t2 - t1) + R (cx (sin t2 - sin t1) - cy (cos t2 - cos t1))].
+// The reference ships only the pair primitives of this method (src/Base_Functions.jl:230-355: distance,
+// contained, intersection) and no driver; containment / tangency are decided like `contained` (<=) and
+// identical discs keep the lower index.  One warp per candidate, lanes over its circles (N <= 64), FP64;
+// the per-circle terms are summed in a fixed order, so the result is deterministic.
+constexpr int kUnionMaxN = 64;
+__global__ void union_area_kernel(const double *__restrict__ X, long long B, int N, double *__restrict__ area)
+{
+    const long long warp_global = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const double two_pi = 6.283185307179586;
+    for (long long b = warp_global; b < B; b += n_warps) {
+        const double *x = X + b * 3 * N;
+        double mine = 0.0;
+        for (int i = lane; i < N; i += 32) {
+            const double cxi = x[i], cyi = x[N + i], Ri = x[2 * N + i];
+            if (!(Ri > 0.0)) continue;
+            double ia[2 * kUnionMaxN], ib[2 * kUnionMaxN]; // covered angular intervals (local memory)
+            int n = 0;
+            bool whole = false;
+            for (int j = 0; j < N && !whole; ++j) {
+                const double Rj = x[2 * N + j];
+                if (j == i || !(Rj > 0.0)) continue;
+                const double dx = x[j] - cxi, dy = x[N + j] - cyi;
+                const double d = hypot(dx, dy);
+                if (d >= Ri + Rj) continue;
+                if (d + Ri <= Rj) { // circle i inside disc j (identical discs: the lower index survives)
+                    if (d + Rj <= Ri && i < j) continue;
+                    whole = true;
+                    break;
+                }
+                if (d + Rj <= Ri) continue; // disc j inside disc i: does not touch i's boundary
+                const double phi = atan2(dy, dx);
+                const double c = (Ri * Ri + d * d - Rj * Rj) / (2.0 * Ri * d);
+                const double alpha = acos(fmax(-1.0, fmin(1.0, c)));
+                double a = fmod(phi - alpha, two_pi);
+                if (a < 0.0) a += two_pi;
+                const double e = a + 2.0 * alpha;
+                if (e > two_pi) {
+                    ia[n] = a; ib[n++] = two_pi;
+                    ia[n] = 0.0; ib[n++] = e - two_pi;
+                } else {
+                    ia[n] = a; ib[n++] = e;
+                }
+            }
+            if (whole) continue;
+            for (int p = 1; p < n; ++p) { // insertion sort by interval start
+                const double ka = ia[p], kb = ib[p];
+                int q = p - 1;
+                while (q >= 0 && ia[q] > ka) {
+                    ia[q + 1] = ia[q];
+                    ib[q + 1] = ib[q];
+                    --q;
+                }
+                ia[q + 1] = ka;
+                ib[q + 1] = kb;
+            }
+            double pos = 0.0, acc = 0.0;
+            for (int p = 0; p <= n; ++p) {
+                const double a = p < n ? ia[p] : two_pi;
+                if (a > pos) { // exposed arc [pos, a]
+                    double s1, c1, s2, c2;
+                    sincos(pos, &s1, &c1);
+                    sincos(a, &s2, &c2);
+                    acc += 0.5 * (Ri * Ri * (a - pos) + Ri * (cxi * (s2 - s1) - cyi * (c2 - c1)));
+                }
+                if (p < n) pos = fmax(pos, ib[p]);
+            }
+            mine += acc;
+        }
+        // fixed-order reduction over the lanes
+        for (int off = 16; off; off >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, off);
+        if (lane == 0) area[b] = mine;
+    }
+}
+cudaError_t launch_union_area(const double *dX, long long B, int N, double *d_area, cudaStream_t s)
+{
+    if (B <= 0) return cudaSuccess;
+    const int block = 128;
+    const int grid = (int)std::min<long long>((B * 32 + block - 1) / block, 148 * 16);
+    union_area_kernel<<<grid, block, 0, s>>>(dX, B, N, d_area);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_fire_step(const unsigned char *cur, unsigned char *nxt, unsigned char *mult, unsigned char *cls,
                              int nx, int ny, unsigned long long seed, unsigned int step, const double *p_dir,
                              int append, unsigned long long *pushed, int *overflow, cudaStream_t s)

@@ -58,6 +58,7 @@ cudaError_t launch_add_points(unsigned char *mult, unsigned char *cls, const int
                               const unsigned char *cell_cls, long long P, int *overflow, cudaStream_t s);
 cudaError_t launch_argmin(const double *obj, const unsigned char *feasible, long long B, int barrier,
                           double *scratch_obj, long long *scratch_idx, int scratch_n, cudaStream_t s);
+cudaError_t launch_union_area(const double *dX, long long B, int N, double *d_area, cudaStream_t s);
 cudaError_t launch_fire_step(const unsigned char *cur, unsigned char *nxt, unsigned char *mult, unsigned char *cls,
                              int nx, int ny, unsigned long long seed, unsigned int step, const double *p_dir,
                              int append, unsigned long long *pushed, int *overflow, cudaStream_t s);

@@ -249,6 +249,13 @@ class CoverageEngine:
         self._check(lib.cov_argmin(self._h, _ptr(X), X.shape[0], 1 if barrier else 0, C.byref(bo), C.byref(bi)))
         return bo.value, bi.value
 
+    def union_area(self, X, N: int) -> np.ndarray:
+        """Exact area of the union of the N discs of every row of X (B, 3N) -- the continuous variant."""
+        X = _f64(X).reshape(-1, 3 * N)
+        out = np.empty(X.shape[0], dtype=np.float64)
+        self._check(lib.cov_union_area_batch(self._h, _ptr(X), X.shape[0], N, _ptr(out)))
+        return out
+
     def eval_batch_device(self, dX: int, B: int, d_obj: int, d_count: int = 0, d_feasible: int = 0):
         """Device pointers (ints); asynchronous on the engine's stream."""
         self._check(lib.cov_eval_batch_device(self._h, C.c_void_p(dX), B, C.c_void_p(d_obj),

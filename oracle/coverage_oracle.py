@@ -170,3 +170,61 @@ def threshold_by_search(R: float) -> float:
     while math.sqrt(t) < R:
         t = math.nextafter(t, math.inf)
     return t
+
+
+# ---- continuous variant: exact area of the union of discs -------------------------
+# PARITY UNPINNED: the reference ships only the circle-circle primitives of a Green's-theorem method
+# (src/Base_Functions.jl:230-355: distance, contained, intersection) and no driver, so there is nothing
+# to compare against except mathematics: closed forms for <= 2 discs and Monte-Carlo estimates.
+def union_area(x) -> float:
+    """Area of the union of the discs [x;y;R] by boundary integration: for every circle the arcs not
+    inside any other disc contribute 1/2 * integral (x dy - y dx)."""
+    x = np.asarray(x, dtype=np.float64)
+    n = len(x) // 3
+    cx, cy, R = x[:n], x[n:2 * n], x[2 * n:]
+    total = 0.0
+    two_pi = 2.0 * math.pi
+    for i in range(n):
+        if not (R[i] > 0):
+            continue
+        covered = []  # angular intervals of circle i inside some other disc
+        whole = False
+        for j in range(n):
+            if j == i or not (R[j] > 0):
+                continue
+            dx, dy = cx[j] - cx[i], cy[j] - cy[i]
+            d = math.hypot(dx, dy)
+            if d >= R[i] + R[j]:
+                continue
+            if d + R[i] <= R[j]:  # circle i inside disc j (identical discs: the lower index survives)
+                if d + R[j] <= R[i] and i < j:
+                    continue
+                whole = True
+                break
+            if d + R[j] <= R[i]:  # disc j inside disc i: does not touch i's boundary
+                continue
+            phi = math.atan2(dy, dx)
+            c = (R[i] * R[i] + d * d - R[j] * R[j]) / (2.0 * R[i] * d)
+            alpha = math.acos(max(-1.0, min(1.0, c)))
+            a = (phi - alpha) % two_pi
+            b = a + 2.0 * alpha
+            if b > two_pi:
+                covered.append((a, two_pi))
+                covered.append((0.0, b - two_pi))
+            else:
+                covered.append((a, b))
+        if whole:
+            continue
+        covered.sort()
+        pos = 0.0
+        arcs = []
+        for a, b in covered:
+            if a > pos:
+                arcs.append((pos, a))
+            pos = max(pos, b)
+        if pos < two_pi:
+            arcs.append((pos, two_pi))
+        for t1, t2 in arcs:
+            total += 0.5 * (R[i] * R[i] * (t2 - t1) +
+                            R[i] * (cx[i] * (math.sin(t2) - math.sin(t1)) - cy[i] * (math.cos(t2) - math.cos(t1))))
+    return total

@@ -642,3 +642,54 @@ def test_fire_automaton_matches_oracle(cov, orc, engine):
     X = rand_candidates(rng, 1000, N)
     X[:, N:2 * N] *= 0.8
     check_against_oracle(cov, orc, engine, X, N, r_max, pts)
+
+
+# ---------------------------------------------------------------- continuous union-area variant
+UNION_RTOL = 1e-9  # measured agreement of the FP64 kernel with the NumPy restatement; north_star allows 1e-5
+
+
+def test_union_area_closed_forms_and_oracle(cov, npo, engine):
+    lens = lambda d: 2 * math.pi - (2 * math.acos(d / 2) - d / 2 * math.sqrt(4 - d * d))  # noqa: E731  two unit discs
+    cases = [
+        ([0, 0, 1.0], math.pi),                                  # one disc
+        ([0, 1, 0, 0, 1, 1.0], lens(1.0)),                        # lens
+        ([0, 0.1, 0, 0, 2, 1.0], 4 * math.pi),                    # contained
+        ([0, 0, 0, 0, 1, 1.0], math.pi),                          # identical
+        ([0, 2, 0, 0, 1, 1.0], 2 * math.pi),                      # externally tangent
+        ([0, 1, 0, 0, 2, 1.0], 4 * math.pi),                      # internally tangent
+        ([0, 5, 0, 0, 1, 2.0], 5 * math.pi),                      # disjoint
+        ([0, 1, 0, 0, 1, 0.0], math.pi),                          # a zero-radius disc
+        ([3, 3, 3, 7, 7, 7, 2, 2, 2.0], 4 * math.pi),             # three identical
+    ]
+    for x, want in cases:
+        n = len(x) // 3
+        got = float(engine.union_area(np.array([x], dtype=np.float64), n)[0])
+        assert abs(got - want) <= UNION_RTOL * max(want, 1.0), (x, got, want)
+        assert abs(npo.union_area(x) - want) <= 1e-12 * max(want, 1.0)
+    rng = np.random.default_rng(4)
+    for n in (1, 2, 5, 20, 64):
+        X = np.concatenate([rng.random((200, 2 * n)) * 120, 2 + rng.random((200, n)) * 30], axis=1)
+        X[:20, :2 * n] = 50 + X[:20, :2 * n] * 0.05  # tight clusters: containment and many crossings
+        got = engine.union_area(X, n)
+        want = np.array([npo.union_area(x) for x in X])
+        assert np.all(np.abs(got - want) <= UNION_RTOL * want), np.max(np.abs(got - want) / want)
+        assert np.all(got <= np.sum(math.pi * X[:, 2 * n:] ** 2, axis=1) * (1 + 1e-12))
+        assert np.all(got >= math.pi * np.max(X[:, 2 * n:], axis=1) ** 2 * (1 - 1e-12))
+    assert cov.AreaCoverageCalculation.unionArea(np.array([0, 1, 0, 0, 1, 1.0]), engine) == pytest.approx(lens(1.0), rel=1e-12)
+    with pytest.raises(cov.CoverageError):
+        engine.union_area(np.zeros((1, 3 * 65)), 65)
+
+
+def test_union_area_vs_fine_grid_count(cov, orc, engine):
+    """The discrete objective converges to the continuous one: on a fine dense grid, cell area x covered
+    cells approaches the union area (inside the domain)."""
+    n = 2048
+    d = 500.0 / n
+    engine.set_grid_full(n, n, d, d)
+    N = 6
+    engine.set_params(N, np.zeros(N), penalty_scale=0.0)
+    rng = np.random.default_rng(8)
+    X = np.concatenate([100 + rng.random((16, 2 * N)) * 300, 10 + rng.random((16, N)) * 25], axis=1)
+    counts = engine.eval_batch(X)["count"]
+    area = engine.union_area(X, N)
+    assert np.all(np.abs(counts * d * d - area) <= 2e-3 * area)

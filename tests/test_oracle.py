@@ -95,3 +95,19 @@ def test_threshold_definition(orc, npo):
         assert math.sqrt(t) >= R and math.sqrt(math.nextafter(t, 0.0)) < R
     assert orc.threshold_by_search(0.0) == 0.0 and orc.threshold_by_search(-1.0) == 0.0
     assert orc.threshold_by_search(float("nan")) == 0.0 and orc.threshold_by_search(math.inf) == math.inf
+
+
+def test_union_area_closed_forms(npo):
+    """Continuous variant (unpinned by the reference: checked against mathematics)."""
+    lens = 2 * math.pi - (2 * math.acos(0.5) - 0.5 * math.sqrt(3.0))
+    assert abs(npo.union_area([0, 0, 1.0]) - math.pi) < 1e-14
+    assert abs(npo.union_area([0, 1, 0, 0, 1, 1.0]) - lens) < 1e-13
+    assert abs(npo.union_area([0, 0.1, 0, 0, 2, 1.0]) - 4 * math.pi) < 1e-13
+    assert abs(npo.union_area([0, 0, 0, 0, 1, 1.0]) - math.pi) < 1e-14
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.random(16) * 50, rng.random(8) * 10 + 2])
+    pts = rng.random((400000, 2)) * 70 - 10
+    cov = np.zeros(len(pts), dtype=bool)
+    for i in range(8):
+        cov |= (pts[:, 0] - x[i]) ** 2 + (pts[:, 1] - x[8 + i]) ** 2 < x[16 + i] ** 2
+    assert abs(npo.union_area(x) - cov.mean() * 4900) < 0.01 * npo.union_area(x)  # Monte-Carlo, 1 %
