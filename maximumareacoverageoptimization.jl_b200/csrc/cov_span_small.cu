@@ -35,7 +35,7 @@ constexpr int kSmallMaxN = 8;
 // all-zero between candidates and idle until phase 2), so it is at least chunk * 24 N bytes.
 __host__ __device__ inline int small_fb_bytes(const GridDesc &g, int N, int chunk)
 {
-    const int fb = round_up(g.ny * g.stride * 4, 16), stage = round_up(chunk * 3 * N * 8, 16);
+    const int fb = round_up(g.ny * (fb_can_swizzle(g) ? g.wpr : g.stride) * 4, 16), stage = round_up(chunk * 3 * N * 8, 16);
     return fb > stage ? fb : stage;
 }
 __host__ __device__ inline int small_warp_bytes(const GridDesc &g, int N, int chunk)
@@ -83,6 +83,9 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
     for (int t2 = lane; t2 < fb_bytes / 16; t2 += 32) reinterpret_cast<uint4 *>(fb)[t2] = make_uint4(0, 0, 0, 0);
     __syncwarp();
 
+    FbLayout fl;
+    fl.swz = fb_can_swizzle(g) ? 7 : 0;
+    fl.stride = fl.swz ? g.wpr : g.stride;
     const long long n_chunks = (B + CHUNK - 1) / CHUNK;
     const int cstride = 3 * N;
     ItemCtx ictx;
@@ -263,7 +266,7 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
 #pragma unroll
                     for (int k = 0; k < kItems; ++k) {
                         const bool sh = (d[k].flags & 2u) != 0;
-                        paint_span<MULTI>(g, fb, planes_s, j[k], lo[k], hi[k], st[k] == kSpan, sh, cnt);
+                        paint_span<MULTI>(g, fb, planes_s, j[k], lo[k], hi[k], st[k] == kSpan, sh, cnt, 1, fl);
                     }
                 };
                 // two items per lane while more than 32 remain, one for the last short stretch (the trip
@@ -297,8 +300,7 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
                             wb = (cb - 1) >> 5;
                         }
                         for (int j = r0 + (int)lane; j <= r1; j += 32) {
-                            uint32_t *frow = fb + (j - 1) * g.stride;
-                            for (int w = wa; w <= wb; ++w) frow[w] = 0u;
+                            for (int w = wa; w <= wb; ++w) fb[fl.at(j - 1, w)] = 0u;
                         }
                     }
                 }
