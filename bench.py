@@ -55,14 +55,19 @@ UNIT = "evals/s"
 WORKLOAD = "C2: 5 UAVs x 1M random candidates/step/GPU, 256x256 synthetic fire grid (BASELINE.json configs[1])"
 
 
-def load_traffic():
-    """DRAM bytes per launch of the bench kernel from the committed ncu capture (profiles/), or None."""
+def load_ncu_capture():
+    """Numbers of the committed ncu capture of the bench kernel (profiles/), or {} for other workloads."""
     p = os.path.join(ROOT, "profiles", "r1_traffic.json")
     if N_UAV == 5 and GRID_N == 256 and B_PER_GPU == 1_000_000 and os.path.exists(p):
         with open(p) as f:
-            d = json.load(f)
-        return d["dram_bytes_read"] + d["dram_bytes_write"]
-    return None
+            return json.load(f)
+    return {}
+
+
+def load_traffic():
+    """DRAM bytes per launch of the bench kernel from the committed ncu capture, or None."""
+    d = load_ncu_capture()
+    return d["dram_bytes_read"] + d["dram_bytes_write"] if d else None
 
 
 def load_peaks():
@@ -365,7 +370,9 @@ def main():
             "issue": {"algorithmic_tests_per_sec_per_gpu": B * tests_per_eval / (kernel_ms * 1e-3),
                       "lane_instr_peak_per_sec": issue_peak,
                       "brute_force_ceiling_tests_per_sec": issue_peak / 6.0,
-                      "frac_of_brute_force_ceiling": B * tests_per_eval / (kernel_ms * 1e-3) / (issue_peak / 6.0)},
+                      "frac_of_brute_force_ceiling": B * tests_per_eval / (kernel_ms * 1e-3) / (issue_peak / 6.0),
+                      "ncu_issue_slot_utilisation": load_ncu_capture().get("issue_slot_utilisation"),
+                      "ncu_warp_instructions_per_candidate": load_ncu_capture().get("warp_instructions_per_candidate")},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * row_bytes, "d2h_bytes_per_step": B * 17,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
