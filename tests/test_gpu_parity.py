@@ -693,3 +693,36 @@ def test_union_area_vs_fine_grid_count(cov, orc, engine):
     counts = engine.eval_batch(X)["count"]
     area = engine.union_area(X, N)
     assert np.all(np.abs(counts * d * d - area) <= 2e-3 * area)
+
+
+def test_two_handles_from_two_threads(cov, orc):
+    """Distinct handles used from distinct threads at the same time (DirectSearch's SetMaxEvals case)."""
+    import threading
+    pts = orc.createPOI(5.0, 5.0, 100.0, 100.0)
+    N = 5
+    r_max = np.full(N, 30 * T)
+    results, errors = {}, []
+
+    def work(k):
+        try:
+            with cov.CoverageEngine(0) as e:
+                e.set_grid_full(100, 100, 5.0, 5.0)
+                e.set_params(N, r_max)
+                X = cov.synth.random_candidates(3000, N, seed=100 + k)
+                outs = [e.eval_batch(X)["obj"].copy() for _ in range(5)]
+                ones = [e.eval_one(X[i]) for i in range(20)]
+                results[k] = (X, outs, ones)
+        except Exception as ex:  # noqa: BLE001
+            errors.append(ex)
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    for k, (X, outs, ones) in results.items():
+        want = orc.eval_batch(X, N, r_max, pts)["obj"]
+        for o in outs:
+            assert np.array_equal(o, want)
+        assert ones == want[:20].tolist()
