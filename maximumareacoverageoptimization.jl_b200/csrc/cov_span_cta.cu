@@ -33,8 +33,10 @@ constexpr int kCtaThreads = 256;
 constexpr int kCtasPerSm = 3;
 
 struct CtaPlan {
-    int fixed_bytes, fb_bytes, band_rows, total_bytes, ctas_per_sm;
+    int fixed_bytes, tab_bytes, fb_bytes, band_rows, total_bytes, ctas_per_sm;
 };
+// unit table: one 32-bit entry (disc << 16 | unit within the disc) per 32-row work unit of a band
+__host__ __device__ inline int cta_tab_bytes(int N, int band_rows) { return round_up(N * ((band_rows + 31) / 32) * 4, 16); }
 __host__ __device__ inline int cta_fixed_bytes(int N)
 {
     return round_up(3 * N * 8, 16) + N * 32 + round_up((N + 1) * 4, 16) + 1024;
@@ -49,8 +51,9 @@ static CtaPlan cta_plan(const GridDesc &g, int N, int smem_per_sm, int band_rows
     int best = 0;
     for (int ctas = (ctas_opt > 0 ? ctas_opt : kCtasPerSm); ctas >= 1; --ctas) {
         const int budget = smem_per_sm / ctas - 1024; // 1 KB per CTA is reserved by the system
-        int rows = (budget - p.fixed_bytes) / row_bytes;
+        int rows = (int)((budget - p.fixed_bytes - 4 * N - 16) / (row_bytes + N / 8.0));
         if (rows > g.ny) rows = g.ny;
+        while (rows > 1 && p.fixed_bytes + cta_tab_bytes(N, rows) + round_up(rows * row_bytes, 16) > budget) --rows;
         if (rows >= std::min(g.ny, 96) || ctas == 1) {
             best = ctas;
             p.band_rows = rows;
@@ -60,7 +63,8 @@ static CtaPlan cta_plan(const GridDesc &g, int N, int smem_per_sm, int band_rows
     p.ctas_per_sm = best;
     if (band_rows_opt > 0 && band_rows_opt < p.band_rows) p.band_rows = band_rows_opt;
     p.fb_bytes = p.band_rows > 0 ? round_up(p.band_rows * row_bytes, 16) : 0;
-    p.total_bytes = p.fixed_bytes + p.fb_bytes;
+    p.tab_bytes = p.band_rows > 0 ? cta_tab_bytes(N, p.band_rows) : 0;
+    p.total_bytes = p.fixed_bytes + p.tab_bytes + p.fb_bytes;
     return p;
 }
 
@@ -80,7 +84,8 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
     SDisc *dp = reinterpret_cast<SDisc *>(smem_raw + round_up(3 * N * 8, 16));
     uint32_t *prefix = reinterpret_cast<uint32_t *>(smem_raw + round_up(3 * N * 8, 16) + N * 32);
     unsigned char *scratch = smem_raw + round_up(3 * N * 8, 16) + N * 32 + round_up((N + 1) * 4, 16);
-    uint32_t *fb = reinterpret_cast<uint32_t *>(scratch + 1024);
+    uint32_t *unit_tab = reinterpret_cast<uint32_t *>(scratch + 1024);
+    uint32_t *fb = reinterpret_cast<uint32_t *>(scratch + 1024 + cta_tab_bytes(N, band_rows));
     // scratch: [0,8) next candidate; [8,16) violation; [16,24) progressive; [24,28) units of the band;
     //          [28,32) unit dispenser; [512, 512 + nwarps*4*8) per-warp counts
     unsigned long long *s_next = reinterpret_cast<unsigned long long *>(scratch);
@@ -159,7 +164,8 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
         // ---- D. bands of framebuffer rows ----
         for (int jb0 = 1; jb0 <= g.ny; jb0 += band_rows) {
             const int jb1 = min(g.ny, jb0 + band_rows - 1);
-            // work units = 32-row blocks of a disc's rows inside the band; prefix[c] = first unit of disc c
+            // work units = 32-row blocks of a disc's rows inside the band; prefix[c] = first unit of disc c,
+            // unit_tab[u] = (disc, unit within the disc)
             if (warp == 0) {
                 uint32_t carry = 0;
                 for (int c0 = 0; c0 < N; c0 += 32) {
@@ -176,7 +182,11 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
                         const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
                         if (lane >= off) incl += v;
                     }
-                    if (c < N) prefix[c + 1] = carry + incl;
+                    if (c < N) {
+                        prefix[c + 1] = carry + incl;
+                        const uint32_t first = carry + incl - n; // this disc's units: table entries
+                        for (uint32_t k = 0; k < n; ++k) unit_tab[first + k] = ((uint32_t)c << 16) | k;
+                    }
                     carry += __shfl_sync(0xffffffffu, incl, 31);
                 }
                 if (lane == 0) {
@@ -196,20 +206,13 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
                     if (u0 >= units) break;
                     const uint32_t u1 = min(u0 + 1, units - 1);
                     const bool has1 = u0 + 1 < units;
-                    // disc of a unit: the largest c with prefix[c] <= u (warp-uniform binary search)
-                    int lo = 0, hi = N - 1;
-                    while (lo < hi) {
-                        const int mid = (lo + hi + 1) >> 1;
-                        if (prefix[mid] <= u0) lo = mid;
-                        else hi = mid - 1;
-                    }
-                    const int c0 = lo;
-                    int c1 = c0;
-                    while (c1 + 1 < N && prefix[c1 + 1] <= u1) ++c1;
+                    // disc and position of a unit: one table entry each (warp-uniform broadcast loads)
+                    const uint32_t e0 = unit_tab[u0], e1 = unit_tab[u1];
+                    const int c0 = (int)(e0 >> 16), c1 = (int)(e1 >> 16);
                     COV_ASSERT(c0 >= 0 && c0 < N && c1 >= 0 && c1 < N);
                     const SDisc d0 = dp[c0], d1 = dp[c1];
-                    const int j0 = max((int)(d0.rows & 0xffffu), jb0) + (int)((u0 - prefix[c0]) << 5) + lane;
-                    const int j1 = max((int)(d1.rows & 0xffffu), jb0) + (int)((u1 - prefix[c1]) << 5) + lane;
+                    const int j0 = max((int)(d0.rows & 0xffffu), jb0) + (int)((e0 & 0xffffu) << 5) + lane;
+                    const int j1 = max((int)(d1.rows & 0xffffu), jb0) + (int)((e1 & 0xffffu) << 5) + lane;
                     const bool in0 = j0 <= min((int)(d0.rows >> 16), jb1);
                     const bool in1 = has1 && j1 <= min((int)(d1.rows >> 16), jb1);
                     const int jj0 = in0 ? j0 : jb0, jj1 = in1 ? j1 : jb0; // any row of the band: result discarded
