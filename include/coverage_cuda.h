@@ -68,7 +68,9 @@ enum {
     COV_OPT_BAND_ROWS = 4,      /* span kernel framebuffer band height in rows; 0 = auto */
     COV_OPT_FORCE_EXACT = 5,    /* 1: span/brute kernels skip the FP32 band and decide every edge in FP64 */
     COV_OPT_CHUNK = 6,          /* host-path pipeline chunk (candidates per H2D/launch/D2H slice); 0 = auto */
-    COV_OPT_TRACE = 7           /* 1: record a per-slice device timeline of every host-path call (cov_get_trace) */
+    COV_OPT_TRACE = 7,          /* 1: record a per-slice device timeline of every host-path call (cov_get_trace) */
+    COV_OPT_ZEROCOPY_OUT = 8    /* 1 (default): the host path's kernels write their results straight into pinned host
+                                   memory; 0: into device buffers, copied back slice by slice */
 };
 
 typedef struct cov_handle cov_handle;
