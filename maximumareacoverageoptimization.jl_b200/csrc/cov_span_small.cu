@@ -2,21 +2,28 @@
 // grid whose union framebuffer fits a warp's share of shared memory (the reference's own
 // configurations: N = 5 on 100 x 100, and BASELINE's 5 x 1M on 256 x 256).
 //
-// Same result as the general span kernel (cov_kernels.cu) -- the count of list entries inside the
+// Same result as the general span kernel (cov_span_cta.cu) -- the count of list entries inside the
 // union of the discs, src/AreaCoverageCalculation.jl:63-110 of /root/reference, plus the objective
-// and constraint outputs -- organised for short candidates:
-//   phase 1  lane k of a warp owns candidate k of a 32- (or 16-) candidate chunk: it reads its
-//            3N doubles, forms the penalty sums and constraint verdicts serially in FP64 (the
-//            reference's own order) and writes one 32-byte record per disc to shared memory.
-//            32 candidates are set up at once instead of one candidate on N of 32 lanes.
-//   phase 2  per candidate, the (disc, row) pairs are FLATTENED over the lanes.  A lane computes
-//            the covered columns [lo, hi] of its row in FP32, in coordinates relative to the
-//            disc's nearest cell (so the FP32 error is ~2^-23 R instead of ~2^-21 * 500 m),
-//            certifies both ends against an error band, and falls back to the exact FP64 walk
-//            only when the band cannot decide.  The interval is OR-ed into the warp's
-//            shared-memory framebuffer with atomicOr; the bits the lane was first to set are
-//            AND-ed with the fire plane words and popcounted: a union count, whatever the order.
-//   phase 3  lane k assembles candidate k's objective; 32 results leave as coalesced stores.
+// and constraint outputs -- organised for short candidates.  Persistent CTAs (one per SM, 15-16
+// warps); the fire planes (TMA bulk copy) and the closure parameters sit in shared memory; every
+// warp works on UNITS of CHUNK candidates taken from an atomic dispenser one unit ahead (the next
+// unit's candidates are prefetched into L2 meanwhile):
+//   phase 1  the unit's candidates are staged in shared memory (in the idle framebuffer region) and
+//            lane k owns candidate k: it forms the penalty sums and constraint verdicts serially in
+//            FP64 (the reference's own order), flags the discs whose bounding boxes touch another
+//            disc, and writes one 32-byte record per disc plus the prefix sums of the discs' row
+//            counts.  CHUNK candidates are set up at once instead of one candidate on N of 32 lanes.
+//   phase 2  per candidate, the (disc, row) pairs are FLATTENED over the lanes, two per lane and
+//            pass (one for the last short stretch).  A lane computes the covered columns [lo, hi] of
+//            its row in FP32, in coordinates relative to the disc's nearest cell (so the FP32 error
+//            is ~2^-23 R instead of ~2^-21 * 500 m), certifies both ends against an error band, and
+//            falls back to the exact FP64 walk only when the band cannot decide.  A disc that touches
+//            no other disc is counted directly (popcount of span & fire words); the others OR their
+//            spans into the warp's shared-memory framebuffer with atomicOr and count the bits they
+//            were first to set: a union count, whatever the order.
+//   phase 3  lane k assembles candidate k's objective; CHUNK results leave as coalesced stores.
+// CHUNK in {32, 16, 8, 4} is chosen per launch (launch_span_small) so that batches too small to give
+// every warp several 32-candidate units still fill the machine.
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdint>
