@@ -726,3 +726,29 @@ def test_two_handles_from_two_threads(cov, orc):
         for o in outs:
             assert np.array_equal(o, want)
         assert ones == want[:20].tolist()
+
+
+@pytest.mark.parametrize("dx,dy,nx,ny", [(0.7, 0.7, 200, 150), (1.3, 0.9, 96, 257), (5.0, 5.0, 100, 100),
+                                          (500 / 256, 500 / 256, 256, 256), (1e-3, 1e-3, 64, 64), (1e4, 1e4, 40, 40)])
+def test_span_vs_exact_kernel_stress(cov, engine, dx, dy, nx, ny):
+    """Randomised stress: the FP32-certified span kernels against the FP64-per-cell exact kernel (itself
+    checked against the oracle above) on lattices with non-representable pitches, tiny and huge scales,
+    many candidates, several swarm sizes."""
+    rng = np.random.default_rng(int(nx * 1000 + ny))
+    fire = rng.random((nx, ny)) < 0.5
+    engine.set_grid_bits(cov.synth.pack_bits(fire), nx, ny, dx, dy)
+    ex, ey = nx * dx, ny * dy
+    for N in (1, 3, 8, 13):
+        B = 6000
+        X = np.concatenate([rng.random((B, N)) * ex * 1.2 - 0.1 * ex, rng.random((B, N)) * ey * 1.2 - 0.1 * ey,
+                            rng.random((B, N)) ** 2 * 0.3 * min(ex, ey)], axis=1)
+        X[:500, :2 * N] = np.rint(X[:500, :2 * N] / dx) * dx          # centres on lattice lines
+        X[:500, 2 * N:] = np.rint(X[:500, 2 * N:] / dx) * dx          # radii multiples of the pitch: ties
+        engine.set_params(N, np.full(N, 0.1 * min(ex, ey)))
+        engine.set_option(cov.OPT_KERNEL, KERNELS["exact"])
+        want = engine.eval_batch(X)
+        for kernel in ("span", "span_general"):
+            engine.set_option(cov.OPT_KERNEL, KERNELS[kernel])
+            got = engine.eval_batch(X)
+            assert np.array_equal(got["count"], want["count"]), (kernel, N, np.flatnonzero(got["count"] != want["count"])[:5])
+            assert np.array_equal(got["obj"], want["obj"])
