@@ -1186,9 +1186,7 @@ static int eval_host(cov_handle *h, const double *X, int64_t B, double *obj, int
         int64_t cn = 0;
         for (int64_t c0 = 0; c0 < wn; c0 += cn, slot ^= 1) {
             const int64_t left = wn - c0;
-            // the last slice is cut in two: the kernel of its first half runs while the second half is copied
             cn = std::min(chunk, left);
-            if (h->chunk == 0 && left <= chunk && left >= 8192) cn = (left * 3 / 4 + 31) / 32 * 32;
             const double *src = X + (size_t)(w0 + c0) * 3 * N;
             double *dst = (double *)h->dX.p + (size_t)c0 * 3 * N;
             if (!in_pinned) {
