@@ -192,6 +192,15 @@ COV_API int cov_eval_one(cov_handle *h, const double *x, double *obj);
 COV_API int cov_argmin(cov_handle *h, const double *X, int64_t B, int32_t barrier, double *best_obj,
                int64_t *best_idx);
 
+/* A whole MADS solve in native code: the batch producer the reference lacks (DirectSearch.jl evaluates one
+ * trial point per call). Settings of TDM_STATIC_opt.optimize (src/TDM_STATIC_opt.jl:118-222): start point x0
+ * (3N), iteration limit n_iter (100 there), the same granularity on every variable (1.0 there), the enabled
+ * constraints of cov_set_params as extreme barrier; x_out = the feasible incumbent if one was found, else x0.
+ * Algorithm: granular-mesh MADS (Audet, Le Digabel & Tribes 2019), 2n Householder poll directions, complete
+ * polling, one launch per poll set. stats (nullable): iterations, evaluations, batches, successes. */
+COV_API int cov_mads_solve(cov_handle *h, const double *x0, int64_t n_iter, double granularity, uint64_t seed,
+                           double *x_out, double *obj_out, int64_t *stats);
+
 /* Covered-cell mask of ONE candidate: nx*ny bytes, 1 where the cell is inside some disc (whether
  * or not it holds entries). Lets the host replay an ordered Float64 sum over a weighted list. */
 COV_API int cov_covered_mask(cov_handle *h, const double *x, uint8_t *mask);

@@ -22,13 +22,20 @@ class _Constraint:
         self._engine = None
         self._progressive = progressive
 
+    # one engine per device serves every stand-alone constraint (creating a handle costs milliseconds; a
+    # constraint only has to re-upload its parameters when another constraint used the engine in between)
+    _shared = {}
+
     def engine(self) -> CoverageEngine:
-        if self._engine is None:
+        slot = _Constraint._shared.get(self._device)
+        if slot is None:
             eng = CoverageEngine(self._device)
             eng.set_grid_full(1, 1, 1.0, 1.0)  # constraints do not look at the cell store
-            self._configure(eng)
-            self._engine = eng
-        return self._engine
+            slot = _Constraint._shared[self._device] = [eng, None]
+        if slot[1] is not self:
+            self._configure(slot[0])
+            slot[1] = self
+        return slot[0]
 
     def batch(self, X) -> np.ndarray:
         X = np.ascontiguousarray(X, dtype=np.float64).reshape(-1, 3 * self.N)

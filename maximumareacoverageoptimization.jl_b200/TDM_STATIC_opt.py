@@ -48,6 +48,16 @@ class AreaMaxObjective:
         self._param_key = None
         return rest
 
+    def native_solver(self, constraints):
+        """A callable (x0, n_iter, granularity, seed) -> (x, objective, stats) running cov_mads_solve with these
+        extreme constraints fused, or None when a constraint cannot be fused or the area is order-dependent."""
+        if self.fuse(constraints):
+            return None
+        res, eng = self._engine()
+        if not eng.grid_info()["area_exact"]:
+            return None
+        return eng.mads_solve
+
     def _engine(self):
         res = self._resident()
         eng = res.sync()

@@ -15,6 +15,7 @@
 #include <functional>
 #include <mutex>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 #include "cov_device.cuh"
 #include "cov_kernels.cuh"
@@ -1304,6 +1305,183 @@ extern "C" int cov_eval_one(cov_handle *h, const double *x, double *obj)
     CK(cudaMemcpyAsync(hres, h->d_obj.p, 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     *obj = *hres;
+    return COV_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// the batched MADS poll driver in native code: the caller of the objective.
+// Same settings as the reference's TDM_STATIC_opt.optimize (src/TDM_STATIC_opt.jl:118-222: iteration
+// limit, granularity on every variable, extreme barrier from the fused constraints, feasible incumbent
+// else the start point) and the same published algorithm as mads.py (granular mesh of Audet, Le Digabel &
+// Tribes 2019: poll size a * 10^b with a in {1, 2, 5}, mesh size max(10^(b - |b - b0|), granularity),
+// 2n directions from a random Householder matrix rounded onto the mesh, complete polling); every poll
+// set is ONE launch through the small-batch path.  DirectSearch.jl's own iterates are not reproducible
+// (unseeded LTMADS), so trajectories are not a parity target; objective values are.
+// ------------------------------------------------------------------------------------------
+namespace {
+struct Rng { // splitmix64 + Box-Muller: self-contained, seedable
+    uint64_t s;
+    uint64_t next()
+    {
+        uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    }
+    double u01() { return ((double)(next() >> 11) + 0.5) * (1.0 / 9007199254740992.0); }
+    double normal() { return std::sqrt(-2.0 * std::log(u01())) * std::cos(6.283185307179586 * u01()); }
+};
+struct MeshVar {
+    double a;
+    int b, b0;
+};
+} // namespace
+
+extern "C" int cov_mads_solve(cov_handle *h, const double *x0, int64_t n_iter, double granularity, uint64_t seed,
+                              double *x_out, double *obj_out, int64_t *stats)
+{
+    if (!h) return fail(nullptr, COV_ERR_INVALID, "NULL handle");
+    DeviceGuard dg(h->device);
+    OK(check_ready(h, "cov_mads_solve"));
+    if (!x0 || !x_out || n_iter < 0 || !(granularity >= 0)) return fail(h, COV_ERR_INVALID, "cov_mads_solve: bad arguments");
+    const int n = 3 * h->o.N;
+    const double g = granularity;
+    auto snap = [g](double v) { return g > 0 ? std::nearbyint(v / g) * g : v; };
+    std::unordered_map<std::string, double> cache;
+    int64_t evaluations = 0, batches = 0, successes = 0, iterations = 0;
+    std::vector<double> P, vals;
+    std::vector<uint8_t> feas;
+    auto key_of = [n](const double *p) { return std::string(reinterpret_cast<const char *>(p), (size_t)n * 8); };
+    // objective with the extreme barrier for the rows of P that are not cached yet
+    auto evaluate = [&](const std::vector<double> &pts, std::vector<double> &f) -> int {
+        const int64_t m = (int64_t)pts.size() / n;
+        f.assign((size_t)m, 0.0);
+        std::vector<int64_t> todo;
+        std::vector<double> Q;
+        for (int64_t k = 0; k < m; ++k) {
+            auto it = cache.find(key_of(&pts[(size_t)k * n]));
+            if (it != cache.end()) f[(size_t)k] = it->second;
+            else {
+                todo.push_back(k);
+                Q.insert(Q.end(), &pts[(size_t)k * n], &pts[(size_t)k * n] + n);
+            }
+        }
+        if (!todo.empty()) {
+            vals.assign(todo.size(), 0.0);
+            feas.assign(todo.size(), 1);
+            recycle_spans(h);
+            OK(eval_host(h, Q.data(), (int64_t)todo.size(), vals.data(), nullptr, feas.data(), nullptr, nullptr));
+            evaluations += (int64_t)todo.size();
+            batches += 1;
+            for (size_t q = 0; q < todo.size(); ++q) {
+                const double v = (feas[q] && vals[q] == vals[q]) ? vals[q] : INFINITY;
+                cache[key_of(&Q[q * n])] = v;
+                f[(size_t)todo[q]] = v;
+            }
+        }
+        return COV_OK;
+    };
+    std::vector<double> x(x0, x0 + n), f;
+    OK(evaluate(x, f));
+    double fx = f[0];
+    bool feasible_found = std::isfinite(fx);
+    std::vector<MeshVar> mesh((size_t)n);
+    for (int i = 0; i < n; ++i) { // initial poll size: about |x0_i| / 10 (at least 1), on the {1, 2, 5} x 10^b ladder
+        const double target = std::max(std::max(std::fabs(x[i]) / 10.0, 1.0), g);
+        const int b = (int)std::floor(std::log10(target));
+        const double mant = target / std::pow(10.0, b);
+        mesh[i] = {mant < 2 ? 1.0 : (mant < 5 ? 2.0 : 5.0), b, b};
+    }
+    Rng rng{seed * 0x9E3779B97F4A7C15ull + 0x1234567ull};
+    std::vector<double> v((size_t)n), H((size_t)n * n), delta((size_t)n), rho((size_t)n);
+    for (int64_t it = 0; it < n_iter; ++it) {
+        ++iterations;
+        for (int i = 0; i < n; ++i) {
+            const double Delta = std::max(mesh[i].a * std::pow(10.0, mesh[i].b), g);
+            delta[i] = std::max(std::pow(10.0, mesh[i].b - std::abs(mesh[i].b - mesh[i].b0)), g);
+            rho[i] = std::max(std::nearbyint(Delta / delta[i]), 1.0);
+        }
+        double nrm = 0;
+        for (int i = 0; i < n; ++i) {
+            v[i] = rng.normal();
+            nrm += v[i] * v[i];
+        }
+        nrm = std::sqrt(nrm);
+        for (int i = 0; i < n; ++i) v[i] /= nrm;
+        P.clear();
+        for (int sgn = 1; sgn >= -1; sgn -= 2)
+            for (int j = 0; j < n; ++j) { // column j of I - 2 v v^T, scaled to the poll-to-mesh ratio, rounded
+                double hmax = 0;
+                for (int i = 0; i < n; ++i) {
+                    H[i] = (i == j ? 1.0 : 0.0) - 2.0 * v[i] * v[j];
+                    hmax = std::max(hmax, std::fabs(H[i]));
+                }
+                bool any = false, moved = false;
+                const size_t at = P.size();
+                P.resize(at + n);
+                for (int i = 0; i < n; ++i) {
+                    const double d = std::nearbyint(rho[i] * H[i] / hmax);
+                    any |= d != 0;
+                    P[at + i] = snap(x[i] + sgn * d * delta[i]);
+                    moved |= P[at + i] != x[i];
+                }
+                if (!any || !moved) P.resize(at);
+            }
+        // drop exact duplicates (keep the first)
+        {
+            std::unordered_map<std::string, int> seen;
+            std::vector<double> U;
+            for (size_t k = 0; k * n < P.size(); ++k)
+                if (seen.emplace(key_of(&P[k * n]), 1).second) U.insert(U.end(), &P[k * n], &P[k * n] + n);
+            P.swap(U);
+        }
+        double best = INFINITY;
+        size_t kb = 0;
+        if (!P.empty()) {
+            OK(evaluate(P, f));
+            for (size_t k = 0; k < f.size(); ++k)
+                if (f[k] < best) {
+                    best = f[k];
+                    kb = k;
+                }
+        }
+        if (best < fx || (!feasible_found && std::isfinite(best))) {
+            std::copy(&P[kb * n], &P[kb * n] + n, x.begin());
+            fx = best;
+            feasible_found = true;
+            ++successes;
+            for (auto &m : mesh) { // enlarge
+                if (m.a == 1.0) m.a = 2.0;
+                else if (m.a == 2.0) m.a = 5.0;
+                else {
+                    m.a = 1.0;
+                    ++m.b;
+                }
+            }
+        } else { // refine; stop when every poll size sits at its granularity
+            bool moved = false;
+            for (auto &m : mesh) {
+                if (g > 0 && m.a * std::pow(10.0, m.b) <= g) continue;
+                if (m.a == 1.0) {
+                    m.a = 5.0;
+                    --m.b;
+                } else if (m.a == 2.0) m.a = 1.0;
+                else m.a = 2.0;
+                moved = true;
+            }
+            if (!moved) break;
+        }
+    }
+    const double *res = feasible_found ? x.data() : x0; // p.x if a feasible incumbent exists, else the start (p.i)
+    std::copy(res, res + n, x_out);
+    if (obj_out) *obj_out = fx;
+    if (stats) {
+        stats[0] = iterations;
+        stats[1] = evaluations;
+        stats[2] = batches;
+        stats[3] = successes;
+    }
     return COV_OK;
 }
 

@@ -241,6 +241,18 @@ class CoverageEngine:
         self._check(lib.cov_eval_one(self._h, _ptr(x), C.byref(v)))
         return v.value
 
+    def mads_solve(self, x0, n_iter: int = 100, granularity: float = 1.0, seed: int = 0):
+        """One MADS solve in native code (cov_mads_solve). Returns (x, objective, stats dict)."""
+        x0 = _f64(x0).ravel()
+        if self.N is None or x0.size != 3 * self.N:
+            raise ValueError("x0 must have 3N entries")
+        out = np.empty_like(x0)
+        obj = C.c_double()
+        st = (C.c_int64 * 4)()
+        self._check(lib.cov_mads_solve(self._h, _ptr(x0), int(n_iter), float(granularity), int(seed) & (2**64 - 1),
+                                       _ptr(out), C.byref(obj), st))
+        return out, obj.value, {"iterations": st[0], "evaluations": st[1], "batches": st[2], "successes": st[3]}
+
     def argmin(self, X, barrier: bool = True):
         X = _f64(X)
         if X.ndim == 1:

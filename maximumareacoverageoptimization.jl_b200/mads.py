@@ -105,13 +105,30 @@ def _snap(x, g):
 
 
 def optimize(input, obj, cons_ext, cons_prog, N_iter, granularity=1.0, seed=None, snap_initial=False,
-             return_stats=False):
+             return_stats=False, native=None):
     """src/TDM_STATIC_opt.jl:118-222.  `obj`: callable x -> float, preferably with `.batch(X)` (and
     `.fuse(constraints)`, see TDM_STATIC_opt.AreaMaxObjective).  `cons_ext`: extreme constraints
     x -> bool (flat list; nested lists as in FullSimulation.jl:86 `[cons_ext, cons3]` are flattened).
     `cons_prog` is accepted and ignored exactly like the reference does (:154-159 is commented out).
-    Returns (result, runtime) -- with return_stats=True also a dict of counters."""
+    Returns (result, runtime) -- with return_stats=True also a dict of counters.
+
+    native: True runs the whole solve inside the library (cov_mads_solve: same algorithm and settings, its own
+    random stream, no Python between polls); it needs an objective made by createObjective on a list with
+    exactly summable weights and constraints that all fuse.  None (default) picks it when that holds."""
     t_start = time.perf_counter()
+    if native is not False and hasattr(obj, "native_solver") and np.isscalar(granularity) and not snap_initial:
+        flat_c = []
+        for c in (cons_ext if isinstance(cons_ext, (list, tuple)) else [cons_ext]):
+            flat_c.extend(c if isinstance(c, (list, tuple)) else [c])
+        solver = obj.native_solver(flat_c)
+        if solver is not None:
+            x, fx, st = solver(np.ascontiguousarray(input, dtype=np.float64).ravel(), int(N_iter), float(granularity),
+                               0 if seed is None else int(seed))
+            runtime = time.perf_counter() - t_start
+            st["objective"] = fx
+            return (x, runtime, st) if return_stats else (x, runtime)
+        if native is True:
+            raise ValueError("native MADS needs fusable constraints and exactly summable weights")
     x0 = np.ascontiguousarray(input, dtype=np.float64).ravel().copy()
     n = x0.size
     rng = np.random.default_rng(seed)

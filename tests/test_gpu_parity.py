@@ -752,3 +752,33 @@ def test_span_vs_exact_kernel_stress(cov, engine, dx, dy, nx, ny):
             got = engine.eval_batch(X)
             assert np.array_equal(got["count"], want["count"]), (kernel, N, np.flatnonzero(got["count"] != want["count"])[:5])
             assert np.array_equal(got["obj"], want["obj"])
+
+
+def test_native_mads_solve(cov, orc):
+    """cov_mads_solve: the whole solve inside the library.  Properties of the reference's settings (integer
+    mesh, extreme barrier, no worse than the start) and the returned objective equals the oracle's value."""
+    CF, OPT, TC, ACC = cov.CellFunctions, cov.TDM_STATIC_opt, cov.TDM_Constraints, cov.AreaCoverageCalculation
+    cells = CF.initialise_POI(CF.Cells(), "static")
+    N, FOV = 5, 100 / 180 * math.pi
+    r_max = np.full(N, 30.0 * T)
+    x0 = cov.Base_Functions.allocate_even_circles(15.0, N, 10 * T, 250.0, 250.0)
+    cells = CF.rmvCoveredPOI(cells, x0)
+    pts = cells.points_of_interest.data.copy()
+    obj = OPT.createObjective(cells, N, r_max)
+    cons3 = TC.create_cons3(ACC.make_circles(x0), FOV, 10 * np.ones(N))
+    f0 = obj(x0)
+    for seed in (1, 2, 3):
+        res, runtime, st = OPT.optimize(x0, obj, [TC.cons1, cons3], [], 100, seed=seed, return_stats=True, native=True)
+        assert st["batches"] >= 2 and st["evaluations"] > 30 and runtime > 0
+        assert np.all(res == np.rint(res)) and orc.cons3(res, x0, T, np.full(N, 10.0))
+        f1 = orc.objective(res, r_max, pts)[0]
+        assert st["objective"] == f1 and f1 < f0
+    # the Python driver and the native one start from the same point and both descend
+    res_py, _, st_py = OPT.optimize(x0, obj, [TC.cons1, cons3], [], 100, seed=1, return_stats=True, native=False)
+    assert st_py["objective"] < f0
+    # a host-only constraint cannot be fused: native=None falls back to the Python driver, native=True refuses
+    res2, _ = OPT.optimize(x0, obj, [TC.cons1, cons3, lambda x: True], [], 20, seed=1)
+    assert np.all(res2 == np.rint(res2)) or np.array_equal(res2, x0)
+    with pytest.raises(ValueError):
+        OPT.optimize(x0, obj, [lambda x: True], [], 5, native=True)
+    cells.close()
