@@ -93,6 +93,20 @@ function argmin_batch(h::Handle, X::Matrix{Float64}; barrier = true)
 end
 
 """
+    mads_solve(h, x0; N_iter = 100, granularity = 1.0, seed = 0)
+
+The whole MADS solve inside the library (same settings as `TDM_STATIC_opt.optimize`, src/TDM_STATIC_opt.jl:118-222;
+the constraints given to `set_params!` act as extreme barrier). Returns `(result, objective, runtime_seconds)`.
+"""
+function mads_solve(h::Handle, x0::Vector{Float64}; N_iter = 100, granularity = 1.0, seed = 0)
+    out = similar(x0); obj = Ref{Float64}(0.0); stats = zeros(Int64, 4)
+    t = @elapsed GC.@preserve x0 out stats check(h, ccall((:cov_mads_solve, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Float64, UInt64, Ptr{Float64}, Ref{Float64}, Ptr{Int64}),
+        h.ptr, x0, N_iter, granularity, seed, out, obj, stats))
+    return out, obj[], t
+end
+
+"""
     createObjective(cells, N, r_max; handle = Handle())
 
 Same signature and value as the reference's `TDM_STATIC_opt.createObjective` (src/TDM_STATIC_opt.jl:82):
