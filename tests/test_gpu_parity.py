@@ -782,3 +782,24 @@ def test_native_mads_solve(cov, orc):
     with pytest.raises(ValueError):
         OPT.optimize(x0, obj, [lambda x: True], [], 5, native=True)
     cells.close()
+
+
+@pytest.mark.parametrize("N", [9, 33, 97, 1024])
+def test_swarm_sizes_cta_kernel_vs_oracle(cov, orc, engine, fire_rows, N):
+    """Swarm sizes just above the small-kernel limit, around the early/lazy fire-word switch (96), and at the
+    library's maximum (1024), on the fire list with duplicates (multi-plane path) and on a dense grid."""
+    rng = np.random.default_rng(N)
+    allp = np.concatenate(fire_rows[:40])
+    r_max = np.full(N, 30 * T)
+    B = 24 if N < 1024 else 3
+    X = np.concatenate([150 + rng.random((B, N)) * 250, 150 + rng.random((B, N)) * 220,
+                        (5 + rng.random((B, N)) * 25) * T], axis=1)
+    engine.set_points(allp, 100, 100, 5.0, 5.0)
+    engine.set_params(N, r_max, sep_min=15.0)
+    check_against_oracle(cov, orc, engine, X, N, r_max, allp, sep_min=15.0)
+    pts = orc.createPOI(5.0, 5.0, 100.0, 100.0)
+    engine.set_grid_full(100, 100, 5.0, 5.0)
+    engine.set_params(N, r_max, sep_min=15.0)
+    check_against_oracle(cov, orc, engine, X, N, r_max, pts, sep_min=15.0)
+    with pytest.raises(cov.CoverageError):
+        engine.set_params(1025, np.zeros(1025))
