@@ -263,6 +263,18 @@ static void recycle_spans(cov_handle *h)
     h->last_call_ms_cache = -1;
 }
 
+// Device-side address of pinned host memory (differs from the host address for some registered buffers);
+// nullptr when the buffer cannot be written from the device.
+static void *device_view(void *host)
+{
+    void *d = nullptr;
+    if (cudaHostGetDevicePointer(&d, host, 0) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    return d;
+}
+
 static bool is_pinned_host(const void *p)
 {
     cudaPointerAttributes a{};
@@ -1206,18 +1218,26 @@ static int eval_host(cov_handle *h, const double *X, int64_t B, double *obj, int
             tr(h->stream);
             EvalOut out{};
             const int64_t g0 = w0 + c0;
-            const bool zc = h->zero_copy_out != 0;
+            bool zc = h->zero_copy_out != 0;
             if (zc) {
                 // results go straight to pinned host memory (the caller's buffer, or the staging block): posted
                 // PCIe writes of 17 B per candidate instead of three D2H copies per slice beside the H2D stream
-                out.obj = obj_p ? obj + g0 : (double *)(so + off_obj) + c0;
-                out.count = !count ? nullptr : (cnt_p ? (long long *)count + g0 : (long long *)(so + off_cnt) + c0);
-                out.feasible = !feasible ? nullptr : (fea_p ? feasible + g0 : (unsigned char *)(so + off_fea) + c0);
-                out.class_count = !class_count ? nullptr
-                                               : (cls_p ? (long long *)class_count + (size_t)g0 * ncls
-                                                        : (long long *)(so + off_cls) + (size_t)c0 * ncls);
-                out.progressive = !progressive ? nullptr : (prg_p ? progressive + g0 : (double *)(so + off_prg) + c0);
-            } else {
+                char *v_obj = (char *)device_view(obj_p ? (void *)obj : (void *)(so + off_obj));
+                char *v_cnt = !count ? nullptr : (char *)device_view(cnt_p ? (void *)count : (void *)(so + off_cnt));
+                char *v_fea = !feasible ? nullptr : (char *)device_view(fea_p ? (void *)feasible : (void *)(so + off_fea));
+                char *v_cls = !class_count ? nullptr : (char *)device_view(cls_p ? (void *)class_count : (void *)(so + off_cls));
+                char *v_prg = !progressive ? nullptr : (char *)device_view(prg_p ? (void *)progressive : (void *)(so + off_prg));
+                if (!v_obj || (count && !v_cnt) || (feasible && !v_fea) || (class_count && !v_cls) || (progressive && !v_prg)) {
+                    zc = false; // a buffer the device cannot address: copy back instead
+                } else {
+                    out.obj = (double *)v_obj + (obj_p ? g0 : c0);
+                    out.count = !count ? nullptr : (long long *)v_cnt + (cnt_p ? g0 : c0);
+                    out.feasible = !feasible ? nullptr : (unsigned char *)v_fea + (fea_p ? g0 : c0);
+                    out.class_count = !class_count ? nullptr : (long long *)v_cls + (size_t)(cls_p ? g0 : c0) * ncls;
+                    out.progressive = !progressive ? nullptr : (double *)v_prg + (prg_p ? g0 : c0);
+                }
+            }
+            if (!zc) {
                 out.obj = (double *)h->d_obj.p + c0;
                 out.count = count ? (long long *)h->d_count.p + c0 : nullptr;
                 out.feasible = feasible ? (unsigned char *)h->d_feas.p + c0 : nullptr;
@@ -1249,7 +1269,8 @@ static int eval_host(cov_handle *h, const double *X, int64_t B, double *obj, int
             tr(zc ? h->stream : h->s_out);
         }
         // end of window: results home, device window reusable
-        CKD(cudaStreamSynchronize(h->zero_copy_out ? h->stream : h->s_out));
+        CKD(cudaStreamSynchronize(h->stream));
+        CKD(cudaStreamSynchronize(h->s_out));
         if (!obj_p) host_copy(h, obj + w0, so + off_obj, (size_t)wn * 8);
         if (!cnt_p) host_copy(h, count + w0, so + off_cnt, (size_t)wn * 8);
         if (!fea_p) host_copy(h, feasible + w0, so + off_fea, (size_t)wn);
