@@ -69,8 +69,12 @@ enum {
     COV_OPT_FORCE_EXACT = 5,    /* 1: span/brute kernels skip the FP32 band and decide every edge in FP64 */
     COV_OPT_CHUNK = 6,          /* host-path pipeline chunk (candidates per H2D/launch/D2H slice); 0 = auto */
     COV_OPT_TRACE = 7,          /* 1: record a per-slice device timeline of every host-path call (cov_get_trace) */
+    COV_OPT_PLANE_MODE = 9,     /* CTA kernel, how fire words are read: -1 auto (default), 0 through L2 only when
+                                   the framebuffer atomic left new bits, 1 through L2 ahead of the atomics,
+                                   2 staged in shared memory band by band with TMA bulk copies */
     COV_OPT_ZEROCOPY_OUT = 8    /* 1 (default): the host path's kernels write their results straight into pinned host
                                    memory; 0: into device buffers, copied back slice by slice */
+    
 };
 
 typedef struct cov_handle cov_handle;

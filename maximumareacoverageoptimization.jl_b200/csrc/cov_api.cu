@@ -352,6 +352,7 @@ extern "C" int cov_create(int device, cov_handle **out)
         return bail(e, "cudaStreamCreate");
     nh->stream = nh->own_stream;
     nh->cfg.kernel = COV_KERNEL_AUTO;
+    nh->cfg.plane_mode = -1;
     nh->cfg.num_sms = prop.multiProcessorCount;
     nh->cfg.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     if ((e = cudaMallocHost(&nh->h_small, 4096 + 3 * kMaxUavs * 8)) != cudaSuccess) return bail(e, "cudaMallocHost");
@@ -435,6 +436,10 @@ extern "C" int cov_set_option(cov_handle *h, int option, int64_t value)
     case COV_OPT_ZEROCOPY_OUT:
         h->zero_copy_out = value != 0;
         return COV_OK;
+    case COV_OPT_PLANE_MODE:
+        if (value < -1 || value > 2) return fail(h, COV_ERR_INVALID, "plane mode must be -1..2");
+        h->cfg.plane_mode = (int)value;
+        return COV_OK;
     }
     return fail(h, COV_ERR_INVALID, "unknown option");
 }
@@ -451,6 +456,7 @@ extern "C" int cov_get_option(const cov_handle *h, int option, int64_t *value)
     case COV_OPT_CHUNK: *value = h->chunk; return COV_OK;
     case COV_OPT_TRACE: *value = h->trace; return COV_OK;
     case COV_OPT_ZEROCOPY_OUT: *value = h->zero_copy_out; return COV_OK;
+    case COV_OPT_PLANE_MODE: *value = h->cfg.plane_mode; return COV_OK;
     }
     return COV_ERR_INVALID;
 }

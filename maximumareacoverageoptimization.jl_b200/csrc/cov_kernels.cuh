@@ -14,6 +14,7 @@ struct LaunchCfg {
     int force_exact;
     int num_sms;
     int max_smem_optin;  // bytes
+    int plane_mode;      // CTA kernel: -1 auto, 0 lazy global, 1 early global, 2 staged per band (TMA)
 };
 
 struct LaunchInfo {

@@ -14,7 +14,9 @@
 //     shared memory); warps take units in pairs from a shared-memory dispenser, find the disc with a
 //     warp-uniform binary search, and every lane handles one row of each unit: two independent
 //     spans per lane, atomicOr into the band, popcount of the newly set bits against the fire
-//     planes (read through L1/L2 with ld.global.nc: the planes are shared by every CTA).
+//     plane, whose rows for the band are staged in shared memory by ONE TMA bulk copy per band
+//     (cp.async.bulk + mbarrier, issued while warp 0 builds the band's unit table); small swarms and
+//     multi-plane stores read the fire words through L1/L2 instead.
 // Persistent grid, up to three 256-thread CTAs per SM so that one candidate's serial phases
 // (dispense, stage, setup, barriers) overlap another's span work; candidates come from an atomic
 // counter.
@@ -33,19 +35,21 @@ constexpr int kCtaThreads = 256;
 constexpr int kCtasPerSm = 3;
 
 struct CtaPlan {
-    int fixed_bytes, tab_bytes, fb_bytes, band_rows, total_bytes, ctas_per_sm;
+    int fixed_bytes, tab_bytes, fb_bytes, plane_bytes, band_rows, total_bytes, ctas_per_sm;
 };
+// how the kernel reads the fire words
+enum { kPlanesLazy = 0, kPlanesEarly = 1, kPlanesStaged = 2 };
 // unit table: one 32-bit entry (disc << 16 | unit within the disc) per 32-row work unit of a band
 __host__ __device__ inline int cta_tab_bytes(int N, int band_rows) { return round_up(N * ((band_rows + 31) / 32) * 4, 16); }
 __host__ __device__ inline int cta_fixed_bytes(int N)
 {
     return round_up(3 * N * 8, 16) + N * 32 + round_up((N + 1) * 4, 16) + 1024;
 }
-static CtaPlan cta_plan(const GridDesc &g, int N, int smem_per_sm, int band_rows_opt, int ctas_opt)
+static CtaPlan cta_plan(const GridDesc &g, int N, int smem_per_sm, int band_rows_opt, int ctas_opt, bool staged)
 {
     CtaPlan p{};
-    p.fixed_bytes = cta_fixed_bytes(N);
-    const int row_bytes = g.stride * 4;
+    p.fixed_bytes = cta_fixed_bytes(N) + (staged ? 32 : 0); // + the band's plane rows and an mbarrier when staged
+    const int row_bytes = g.stride * 4 * (staged ? 2 : 1);
     // as many co-resident CTAs as possible (they overlap each other's serial phases), as long as a
     // band still holds a useful number of rows
     int best = 0;
@@ -53,7 +57,8 @@ static CtaPlan cta_plan(const GridDesc &g, int N, int smem_per_sm, int band_rows
         const int budget = smem_per_sm / ctas - 1024; // 1 KB per CTA is reserved by the system
         int rows = (int)((budget - p.fixed_bytes - 4 * N - 16) / (row_bytes + N / 8.0));
         if (rows > g.ny) rows = g.ny;
-        while (rows > 1 && p.fixed_bytes + cta_tab_bytes(N, rows) + round_up(rows * row_bytes, 16) > budget) --rows;
+        if (staged && rows < g.ny) rows &= ~3; // bands start on 16-byte boundaries of the plane
+        while (rows > 1 && p.fixed_bytes + cta_tab_bytes(N, rows) + round_up(rows * row_bytes, 16) + 32 > budget) rows -= staged ? 4 : 1;
         if (rows >= std::min(g.ny, 96) || ctas == 1) {
             best = ctas;
             p.band_rows = rows;
@@ -61,14 +66,15 @@ static CtaPlan cta_plan(const GridDesc &g, int N, int smem_per_sm, int band_rows
         }
     }
     p.ctas_per_sm = best;
-    if (band_rows_opt > 0 && band_rows_opt < p.band_rows) p.band_rows = band_rows_opt;
-    p.fb_bytes = p.band_rows > 0 ? round_up(p.band_rows * row_bytes, 16) : 0;
+    if (band_rows_opt > 0 && band_rows_opt < p.band_rows) p.band_rows = staged ? std::max(4, band_rows_opt & ~3) : band_rows_opt;
+    p.fb_bytes = p.band_rows > 0 ? round_up(p.band_rows * g.stride * 4, 16) : 0;
+    p.plane_bytes = staged && p.band_rows > 0 ? round_up(p.band_rows * g.stride * 4, 16) + 16 : 0;
     p.tab_bytes = p.band_rows > 0 ? cta_tab_bytes(N, p.band_rows) : 0;
-    p.total_bytes = p.fixed_bytes + p.tab_bytes + p.fb_bytes;
+    p.total_bytes = p.fixed_bytes + p.tab_bytes + p.fb_bytes + p.plane_bytes;
     return p;
 }
 
-template <bool MULTI, bool EARLY>
+template <bool MULTI, int PLANES>
 __global__ void __launch_bounds__(kCtaThreads, kCtasPerSm)
 span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjParams o,
                 const double *__restrict__ X, long long B, EvalOut out, unsigned long long *counter,
@@ -95,6 +101,14 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
     uint32_t *s_disp = reinterpret_cast<uint32_t *>(scratch + 28);
     unsigned long long *s_cnt = reinterpret_cast<unsigned long long *>(scratch + 512);
 
+    // staged planes: the band's rows of the fire plane, brought in by one TMA bulk copy per band
+    uint32_t *plane_s = fb + fb_bytes / 4;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(plane_s + fb_bytes / 4);
+    uint32_t bar_phase = 0;
+    if (PLANES == kPlanesStaged && tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     for (int t = tid; t < fb_bytes / 16; t += kCtaThreads) reinterpret_cast<uint4 *>(fb)[t] = make_uint4(0, 0, 0, 0);
 
     for (;;) {
@@ -164,6 +178,13 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
         // ---- D. bands of framebuffer rows ----
         for (int jb0 = 1; jb0 <= g.ny; jb0 += band_rows) {
             const int jb1 = min(g.ny, jb0 + band_rows - 1);
+            if (PLANES == kPlanesStaged && tid == 32) {
+                // rows jb0..jb1 of the plane are contiguous; (jb0 - 1) * stride is a multiple of 4 words
+                const uint32_t words = (uint32_t)round_up((jb1 - jb0 + 1) * g.stride, 4);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // earlier generic reads of plane_s
+                mbar_expect_tx(bar, words * 4);
+                bulk_g2s(plane_s, g.planes + (size_t)(jb0 - 1) * g.stride, words * 4, bar);
+            }
             // work units = 32-row blocks of a disc's rows inside the band; prefix[c] = first unit of disc c,
             // unit_tab[u] = (disc, unit within the disc)
             if (warp == 0) {
@@ -197,6 +218,12 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
             }
             __syncthreads();
             const uint32_t units = *s_units;
+            if (PLANES == kPlanesStaged) {
+                mbar_wait(bar, bar_phase);
+                bar_phase ^= 1u;
+            }
+            // paint_span indexes planes by grid row: shift the band buffer so that row jb0 lands on its row 0
+            const uint32_t *planes_eff = PLANES == kPlanesStaged ? plane_s - (size_t)(jb0 - 1) * g.stride : g.planes;
             if (units != 0) {
                 // warps take units in pairs from the CTA's dispenser: two independent spans per lane
                 for (;;) {
@@ -238,8 +265,8 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
                         lo1 = l2;
                         hi1 = h2;
                     }
-                    paint_span<MULTI, false, true, EARLY>(g, fb, g.planes, jj0, lo0, hi0, st0 == kSpan, true, cnt, jb0);
-                    paint_span<MULTI, false, true, EARLY>(g, fb, g.planes, jj1, lo1, hi1, st1 == kSpan, true, cnt, jb0);
+                    paint_span<MULTI, PLANES == kPlanesStaged, true, PLANES == kPlanesEarly>(g, fb, planes_eff, jj0, lo0, hi0, st0 == kSpan, true, cnt, jb0);
+                    paint_span<MULTI, PLANES == kPlanesStaged, true, PLANES == kPlanesEarly>(g, fb, planes_eff, jj1, lo1, hi1, st1 == kSpan, true, cnt, jb0);
                 }
             }
             __syncthreads();
@@ -289,20 +316,27 @@ cudaError_t launch_span_cta(const GridDesc &g, const ObjParams &o, const LaunchC
                             long long B, const EvalOut &out, unsigned long long *counter, cudaStream_t stream,
                             LaunchInfo *info)
 {
-    const CtaPlan p = cta_plan(g, o.N, cfg.max_smem_optin + 1024, cfg.band_rows, cfg.ctas_per_sm);
-    if (p.band_rows < 1) return cudaErrorInvalidConfiguration;
     const bool multi = !(g.n_planes == 1 && g.n_classes == 1 && g.plane_mult[0] == 1);
+    // how the fire words are read: staged per band by TMA (single plane), else through L1/L2 -- requested
+    // ahead of the framebuffer atomics for moderate swarms, only when the atomic left new bits for dense ones
+    // (measured, B200: staging wins from a few dozen discs per candidate on -- C3 +6 %, C4 +27 % -- and loses
+    // for a handful of discs on a big grid, where most of a staged band is never looked at)
+    int mode = multi ? kPlanesLazy : (cfg.plane_mode >= 0 ? cfg.plane_mode : (o.N >= 16 ? kPlanesStaged : kPlanesEarly));
+    if (multi) mode = kPlanesLazy;
+    CtaPlan p = cta_plan(g, o.N, cfg.max_smem_optin + 1024, cfg.band_rows, cfg.ctas_per_sm, mode == kPlanesStaged);
+    if (mode == kPlanesStaged && p.band_rows < 4) {
+        mode = o.N <= 96 ? kPlanesEarly : kPlanesLazy;
+        p = cta_plan(g, o.N, cfg.max_smem_optin + 1024, cfg.band_rows, cfg.ctas_per_sm, false);
+    }
+    if (p.band_rows < 1) return cudaErrorInvalidConfiguration;
     const int grid = (int)std::min<long long>(B, (long long)cfg.num_sms * p.ctas_per_sm);
     if (info) {
         info->grid = grid;
         info->block = kCtaThreads;
         info->smem_bytes = p.total_bytes;
         info->band_rows = p.band_rows;
-        info->planes_in_smem = 0;
+        info->planes_in_smem = mode == kPlanesStaged;
     }
-    // moderate swarms: request the fire words ahead of the framebuffer atomics; dense swarms (their discs
-    // cover the domain more than once over): only read a fire word when the atomic left new bits
-    const bool early = !multi && o.N <= 96;
     cudaError_t err;
 #define COV_LAUNCH_CTA(M, E)                                                                                      \
     do {                                                                                                          \
@@ -313,9 +347,10 @@ cudaError_t launch_span_cta(const GridDesc &g, const ObjParams &o, const LaunchC
                                                                             cfg.force_exact, p.band_rows,         \
                                                                             p.fb_bytes);                          \
     } while (0)
-    if (multi) COV_LAUNCH_CTA(true, false);
-    else if (early) COV_LAUNCH_CTA(false, true);
-    else COV_LAUNCH_CTA(false, false);
+    if (multi) COV_LAUNCH_CTA(true, kPlanesLazy);
+    else if (mode == kPlanesStaged) COV_LAUNCH_CTA(false, kPlanesStaged);
+    else if (mode == kPlanesEarly) COV_LAUNCH_CTA(false, kPlanesEarly);
+    else COV_LAUNCH_CTA(false, kPlanesLazy);
 #undef COV_LAUNCH_CTA
     return cudaGetLastError();
 }
