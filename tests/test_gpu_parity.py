@@ -803,3 +803,29 @@ def test_swarm_sizes_cta_kernel_vs_oracle(cov, orc, engine, fire_rows, N):
     check_against_oracle(cov, orc, engine, X, N, r_max, pts, sep_min=15.0)
     with pytest.raises(cov.CoverageError):
         engine.set_params(1025, np.zeros(1025))
+
+
+def test_device_path_misaligned_and_odd_batches(cov, orc, engine):
+    """cov_eval_batch_device with a candidate pointer that is only 8-byte aligned, batch sizes that are not
+    multiples of the unit size, and every optional output switched off."""
+    pts = orc.createPOI(5.0, 5.0, 100.0, 100.0)
+    engine.set_grid_full(100, 100, 5.0, 5.0)
+    N = 5
+    r_max = np.full(N, 30 * T)
+    engine.set_params(N, r_max)
+    for B in (1, 31, 127, 129, 1001, 4097, 70001):
+        X = cov.synth.random_candidates(B, N, seed=B)
+        want = orc.eval_batch(X[:min(B, 1500)], N, r_max, pts)
+        raw = engine.device_alloc(B * 3 * N * 8 + 16)
+        d_obj = engine.device_alloc(B * 8)
+        for shift in (0, 8):
+            engine.memcpy_h2d(raw + shift, X)
+            engine.eval_batch_device(raw + shift, B, d_obj)  # no count, no feasibility
+            obj = np.empty(B)
+            engine.memcpy_d2h(obj, d_obj)
+            engine.sync()
+            assert np.array_equal(obj[:len(want["obj"])], want["obj"]), (B, shift)
+        only = engine.eval_batch(X, want_count=False, want_feasible=False)
+        assert set(only) == {"obj"} and np.array_equal(only["obj"], obj)
+        engine.device_free(raw)
+        engine.device_free(d_obj)
