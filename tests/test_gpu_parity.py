@@ -829,3 +829,25 @@ def test_device_path_misaligned_and_odd_batches(cov, orc, engine):
         assert set(only) == {"obj"} and np.array_equal(only["obj"], obj)
         engine.device_free(raw)
         engine.device_free(d_obj)
+
+
+def test_bench_line_contract(cov):
+    """bench.py runs end to end on one GPU and prints ONE JSON line with the contract's keys."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "3", "--warmup", "3", "--batch", "50000",
+                        "--cpu-seconds", "0.5"], capture_output=True, text=True, timeout=280, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["value"] > 0 and d["gpu_launches"] == 3
+    assert d["roofline"]["bound"] == "hbm" and 0 < d["roofline"]["frac"] < 1.5
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["parity_on_sample"] is True
+    assert d["e2e"]["h2d_bytes_per_step"] == 50000 * 120 and d["e2e"]["value"] > 0
