@@ -10,9 +10,9 @@
 //     lane forms the order-dependent penalty sum;
 //   * the union framebuffer lives in shared memory as a BAND of grid rows (the whole grid when it
 //     fits: 1024 x 33 words = 132 KB; 427-row bands for 4096^2);
-//   * per band the work is cut into units of 32 rows of one disc (prefix sums of the unit counts in
-//     shared memory); warps take units in pairs from a shared-memory dispenser, find the disc with a
-//     warp-uniform binary search, and every lane handles one row of each unit: two independent
+//   * per band the work is cut into units of 32 rows of one disc (a unit -> disc table built by a
+//     CTA-wide scan); warps take units in pairs from a shared-memory dispenser and every lane handles
+//     one row of each unit: two independent
 //     spans per lane, atomicOr into the band, popcount of the newly set bits against the fire
 //     plane, whose rows for the band are staged in shared memory by ONE TMA bulk copy per band
 //     (cp.async.bulk + mbarrier, issued while warp 0 builds the band's unit table); small swarms and
@@ -88,17 +88,16 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
     const int cstride = 3 * N;
     double *stage = reinterpret_cast<double *>(smem_raw);
     SDisc *dp = reinterpret_cast<SDisc *>(smem_raw + round_up(3 * N * 8, 16));
-    uint32_t *prefix = reinterpret_cast<uint32_t *>(smem_raw + round_up(3 * N * 8, 16) + N * 32);
     unsigned char *scratch = smem_raw + round_up(3 * N * 8, 16) + N * 32 + round_up((N + 1) * 4, 16);
     uint32_t *unit_tab = reinterpret_cast<uint32_t *>(scratch + 1024);
     uint32_t *fb = reinterpret_cast<uint32_t *>(scratch + 1024 + cta_tab_bytes(N, band_rows));
-    // scratch: [0,8) next candidate; [8,16) violation; [16,24) progressive; [24,28) units of the band;
-    //          [28,32) unit dispenser; [512, 512 + nwarps*4*8) per-warp counts
+    // scratch: [0,8) next candidate; [8,16) violation; [16,24) progressive; [28,32) unit dispenser;
+    //          [32,64) per-warp totals of the unit scan; [512, 512 + nwarps*4*8) per-warp counts
     unsigned long long *s_next = reinterpret_cast<unsigned long long *>(scratch);
     double *s_viol = reinterpret_cast<double *>(scratch + 8);
     double *s_prog = reinterpret_cast<double *>(scratch + 16);
-    uint32_t *s_units = reinterpret_cast<uint32_t *>(scratch + 24);
     uint32_t *s_disp = reinterpret_cast<uint32_t *>(scratch + 28);
+    uint32_t *s_wtot = reinterpret_cast<uint32_t *>(scratch + 32); // per-warp unit totals of a scan pass
     unsigned long long *s_cnt = reinterpret_cast<unsigned long long *>(scratch + 512);
 
     // staged planes: the band's rows of the fire plane, brought in by one TMA bulk copy per band
@@ -112,7 +111,7 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
     for (int t = tid; t < fb_bytes / 16; t += kCtaThreads) reinterpret_cast<uint4 *>(fb)[t] = make_uint4(0, 0, 0, 0);
 
     for (;;) {
-        __syncthreads(); // previous candidate fully retired (stage/dp/prefix/scratch reusable, fb clean)
+        __syncthreads(); // previous candidate fully retired (stage/dp/scratch reusable, fb clean)
         if (tid == 0) *s_next = atomicAdd(counter, 1ull);
         __syncthreads();
         const long long cand = (long long)*s_next;
@@ -185,39 +184,38 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
                 mbar_expect_tx(bar, words * 4);
                 bulk_g2s(plane_s, g.planes + (size_t)(jb0 - 1) * g.stride, words * 4, bar);
             }
-            // work units = 32-row blocks of a disc's rows inside the band; prefix[c] = first unit of disc c,
-            // unit_tab[u] = (disc, unit within the disc)
-            if (warp == 0) {
-                uint32_t carry = 0;
-                for (int c0 = 0; c0 < N; c0 += 32) {
-                    const int c = c0 + lane;
-                    uint32_t n = 0;
-                    if (c < N) {
-                        const uint32_t rows = dp[c].rows;
-                        const int r0 = max((int)(rows & 0xffffu), jb0), r1 = min((int)(rows >> 16), jb1);
-                        n = r1 >= r0 ? (uint32_t)((r1 - r0 + 32) >> 5) : 0u;
-                    }
-                    uint32_t incl = n;
+            // work units = 32-row blocks of a disc's rows inside the band; unit_tab[u] = (disc, unit within the
+            // disc).  All warps take part: 256 discs per pass, warp-level scans chained through shared memory.
+            if (tid == 0) *s_disp = 0; // the dispenser of this band (its last user finished before the band ended)
+            uint32_t units = 0;        // running total, the same in every thread
+            for (int cb = 0; cb < N; cb += kCtaThreads) {
+                const int c = cb + tid;
+                uint32_t n = 0;
+                if (c < N) {
+                    const uint32_t rows = dp[c].rows;
+                    const int r0 = max((int)(rows & 0xffffu), jb0), r1 = min((int)(rows >> 16), jb1);
+                    n = r1 >= r0 ? (uint32_t)((r1 - r0 + 32) >> 5) : 0u;
+                }
+                uint32_t incl = n;
 #pragma unroll
-                    for (int off = 1; off < 32; off <<= 1) {
-                        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
-                        if (lane >= off) incl += v;
-                    }
-                    if (c < N) {
-                        prefix[c + 1] = carry + incl;
-                        const uint32_t first = carry + incl - n; // this disc's units: table entries
-                        for (uint32_t k = 0; k < n; ++k) unit_tab[first + k] = ((uint32_t)c << 16) | k;
-                    }
-                    carry += __shfl_sync(0xffffffffu, incl, 31);
+                for (int off = 1; off < 32; off <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
+                    if (lane >= off) incl += v;
                 }
-                if (lane == 0) {
-                    prefix[0] = 0;
-                    *s_units = carry;
-                    *s_disp = 0;
+                if (lane == 31) s_wtot[warp] = incl;
+                __syncthreads();
+                uint32_t before = 0, all = 0;
+#pragma unroll
+                for (int w = 0; w < nwarps; ++w) {
+                    const uint32_t v = s_wtot[w];
+                    all += v;
+                    before += (w < warp) ? v : 0u;
                 }
+                const uint32_t first = units + before + incl - n; // this disc's units: table entries
+                for (uint32_t k = 0; k < n; ++k) unit_tab[first + k] = ((uint32_t)c << 16) | k;
+                units += all;
+                __syncthreads(); // table entries visible; s_wtot reusable
             }
-            __syncthreads();
-            const uint32_t units = *s_units;
             if (PLANES == kPlanesStaged) {
                 mbar_wait(bar, bar_phase);
                 bar_phase ^= 1u;
@@ -281,8 +279,8 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
                 cls_total[k] += cnt[k];
                 cnt[k] = 0;
             }
-            // the next band's prefix writes wait for everyone at the __syncthreads above; the clear is
-            // ordered against the next band's painting by the __syncthreads after its prefix scan
+            // the next band's table writes wait for everyone at the __syncthreads above; the clear is ordered
+            // against the next band's painting by the __syncthreads of its unit scan
         }
 
         // ---- E. reduce the counts, assemble, write ----
