@@ -383,8 +383,10 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             rate, nthr, n, dt, ref, Xc, pts = cpu_port_rate(cov, bits, d, r_max, args.cpu_seconds)
             got = eng.eval_batch(Xc)
+            rate1, _, n1, dt1, _, _, _ = cpu_port_rate(cov, bits, d, r_max, min(3.0, args.cpu_seconds / 4), threads=1)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": nthr, "kind": "port",
                                     "sample": f"{n} candidates of the same workload in {dt:.1f} s",
+                                    "value_1_thread": rate1, "sample_1_thread": f"{n1} candidates in {dt1:.1f} s",
                                     "parity_on_sample": bool(np.array_equal(got["count"], ref["count"]) and
                                                              np.array_equal(got["obj"], ref["obj"]))}
         print(json.dumps(line))
