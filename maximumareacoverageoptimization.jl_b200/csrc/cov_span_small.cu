@@ -53,8 +53,10 @@ __host__ __device__ inline int small_warp_bytes(const GridDesc &g, int N, int ch
 }
 __host__ __device__ inline int small_param_bytes(int N) { return round_up(5 * N * 8, 16); }
 
-template <bool MULTI, int CHUNK>
-__global__ void __launch_bounds__(512, 1)
+// MAXW: the most warps a CTA of this instantiation may have (20: <= 102 registers per thread, no spills;
+// 24: <= 85, a few spilled bytes -- worth it when the per-warp shared memory is small enough for 24 warps)
+template <bool MULTI, int CHUNK, int MAXW>
+__global__ void __launch_bounds__(MAXW * 32, 1)
 span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjParams o,
                   const double *__restrict__ X, long long B, EvalOut out, unsigned long long *counter,
                   int force_exact)
@@ -360,7 +362,7 @@ bool span_small_applies(const GridDesc &g, int N, const LaunchCfg &cfg, long lon
     for (int chunk : {32, 16}) {
         const int per = small_warp_bytes(g, N, chunk);
         int w = (cfg.max_smem_optin - planes_bytes - small_param_bytes(N) - 16) / per;
-        w = std::min(w, 16); // __launch_bounds__(512): 16 warps, <= 128 registers per thread
+        w = std::min(w, 24); // the 24-warp instantiation (launch_small_variant picks 20 or 24 by this count)
         if (cfg.warps_per_cta > 0) w = std::min(w, cfg.warps_per_cta);
         // prefer the 32-candidate chunk unless the 16-candidate one buys >= 25 % more warps
         if (w >= 4 && (best_w == 0 || w * 4 >= best_w * 5)) {
@@ -390,7 +392,7 @@ bool span_small_applies(const GridDesc &g, int N, const LaunchCfg &cfg, long lon
     return true;
 }
 
-template <bool M, int C>
+template <bool M, int C, int MAXW>
 static cudaError_t launch_small_variant(const GridDesc &g, const ObjParams &o, const LaunchCfg &cfg, const double *dX,
                                         long long B, const EvalOut &out, unsigned long long *counter,
                                         cudaStream_t stream, int grid, int warps, int smem)
@@ -400,11 +402,11 @@ static cudaError_t launch_small_variant(const GridDesc &g, const ObjParams &o, c
     int dev = 0;
     (void)cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || smem > configured_smem[dev]) {
-        cudaError_t err = cudaFuncSetAttribute(span_small_kernel<M, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t err = cudaFuncSetAttribute(span_small_kernel<M, C, MAXW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (err != cudaSuccess) return err;
         if (dev >= 0 && dev < 64) configured_smem[dev] = smem;
     }
-    span_small_kernel<M, C><<<grid, warps * 32, smem, stream>>>(g, o, dX, B, out, counter, cfg.force_exact);
+    span_small_kernel<M, C, MAXW><<<grid, warps * 32, smem, stream>>>(g, o, dX, B, out, counter, cfg.force_exact);
     return cudaGetLastError();
 }
 
@@ -425,8 +427,10 @@ cudaError_t launch_span_small(const GridDesc &g, const ObjParams &o, const Launc
         info->band_rows = g.ny;
         info->planes_in_smem = 1;
     }
-#define COV_SMALL_CASE(M, C) \
-    case C: return launch_small_variant<M, C>(g, o, cfg, dX, B, out, counter, stream, grid, warps, smem)
+#define COV_SMALL_CASE(M, C)                                                                                     \
+    case C:                                                                                                      \
+        return warps > 20 ? launch_small_variant<M, C, 24>(g, o, cfg, dX, B, out, counter, stream, grid, warps, smem) \
+                          : launch_small_variant<M, C, 20>(g, o, cfg, dX, B, out, counter, stream, grid, warps, smem)
     if (multi) {
         switch (chunk) {
             COV_SMALL_CASE(true, 32);
