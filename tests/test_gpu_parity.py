@@ -851,3 +851,34 @@ def test_bench_line_contract(cov):
     assert d["roofline"]["bound"] == "hbm" and 0 < d["roofline"]["frac"] < 1.5
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["parity_on_sample"] is True
     assert d["e2e"]["h2d_bytes_per_step"] == 50000 * 120 and d["e2e"]["value"] > 0
+
+
+@pytest.mark.parametrize("n,N,B", [(1024, 50, 100_000), (4096, 200, 4_000)])
+def test_c3_c4_span_vs_brute_at_scale(cov, engine, n, N, B):
+    """BASELINE's large shapes on many candidates: the CTA span kernel against the brute-force kernel (every
+    cell of every non-empty fire word x every disc; itself checked against the oracle on small samples above).
+    Candidates come from the device-side Philox generator, as BASELINE.md prescribes for C4."""
+    d = 500.0 / n
+    bits, _ = cov.synth.fire_grid(n)
+    engine.set_grid_bits(bits, n, n, d, d)
+    engine.set_params(N, np.full(N, 30 * T), sep_min=15.0)
+    dX = engine.device_alloc(B * 3 * N * 8)
+    outs = {}
+    engine.generate_candidates(dX, B, N, seed=77)
+    for name in ("span", "brute"):
+        engine.set_option(cov.OPT_KERNEL, KERNELS[name])
+        d_obj, d_cnt, d_fe = engine.device_alloc(B * 8), engine.device_alloc(B * 8), engine.device_alloc(B)
+        engine.eval_batch_device(dX, B, d_obj, d_cnt, d_fe)
+        obj, cnt, fe = np.empty(B), np.empty(B, dtype=np.int64), np.empty(B, dtype=np.uint8)
+        engine.memcpy_d2h(obj, d_obj)
+        engine.memcpy_d2h(cnt, d_cnt)
+        engine.memcpy_d2h(fe, d_fe)
+        engine.sync()
+        outs[name] = (obj, cnt, fe)
+        for p in (d_obj, d_cnt, d_fe):
+            engine.device_free(p)
+    engine.device_free(dX)
+    assert np.array_equal(outs["span"][1], outs["brute"][1])
+    assert np.array_equal(outs["span"][0], outs["brute"][0])
+    assert np.array_equal(outs["span"][2], outs["brute"][2])
+    assert outs["span"][1].min() > 0
