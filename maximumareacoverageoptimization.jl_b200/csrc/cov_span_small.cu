@@ -183,7 +183,9 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
             }
             my_feas = !bad;
             uint32_t run = 0;
-            unsigned long long plo = ~0ull, phi = ~0ull; // 8 x u16 inclusive prefixes; unused slots 0xffff
+            // 8 x u16 inclusive prefixes; unused slots 0x7fff (above every item index, and small enough for the
+            // packed compare of phase 2)
+            unsigned long long plo = 0x7fff7fff7fff7fffull, phi = 0x7fff7fff7fff7fffull;
 #pragma unroll 1
             for (int c = 0; c < N; ++c) {
                 SDisc d;
@@ -218,10 +220,8 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
 
         for (int kc = 0; kc < in_chunk; ++kc) {
             const uint4 pq = prefix[kc];
-            uint32_t pre[kSmallMaxN] = {pq.x & 0xffffu, pq.x >> 16, pq.y & 0xffffu, pq.y >> 16,
-                                        pq.z & 0xffffu, pq.z >> 16, pq.w & 0xffffu, pq.w >> 16};
-            const uint32_t total = pre[kSmallMaxN - 1] & 0x7fffu; // number of items (slot 7, see phase 1)
-            const bool any_shared = (pre[kSmallMaxN - 1] & 0x8000u) != 0;
+            const uint32_t total = (pq.w >> 16) & 0x7fffu; // number of items (slot 7, see phase 1)
+            const bool any_shared = (pq.w >> 31) != 0;
             const SDisc *cdp = dp + kc * N;
             ictx.xrow = X + (base + kc) * cstride;
             uint32_t cnt[MULTI ? kMaxClasses : 1];
@@ -242,14 +242,15 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
                         const uint32_t t = tb + 32 * k + lane;
                         has[k] = t < total;
                         tt[k] = has[k] ? t : tb; // an idle slot shadows item tb, result discarded
-                        c[k] = 0;
+                        // disc index = number of inclusive prefixes <= t among slots 0..6, all seven compared at
+                        // once: every 16-bit field of (0x8000 | t) - prefix stays within its field (both sides
+                        // are below 0x8000) and keeps bit 15 exactly when t >= prefix.  Slot 7 (total | flag) may
+                        // borrow out of the top of its word, which harms nothing, and is masked out.
+                        const uint32_t rep = tt[k] * 0x10001u + 0x80008000u;
+                        const uint32_t x0 = rep - pq.x, x1 = rep - pq.y, x2 = rep - pq.z, x3 = rep - pq.w;
+                        c[k] = __popc((x0 & 0x80008000u) | ((x1 & 0x80008000u) >> 1) | ((x2 & 0x80008000u) >> 2) |
+                                      ((x3 & 0x00008000u) >> 3));
                     }
-                    // disc index = number of inclusive prefixes <= t (non-decreasing; unused slots 0xffff).
-                    // (A warp-uniform switch on N into a fall-through chain of N - 1 compares measured slower.)
-#pragma unroll
-                    for (int q = 0; q < kSmallMaxN - 1; ++q)
-#pragma unroll
-                        for (int k = 0; k < kItems; ++k) c[k] += (tt[k] >= pre[q]) ? 1 : 0;
 #pragma unroll
                     for (int k = 0; k < kItems; ++k) {
                         COV_ASSERT(c[k] < N);
