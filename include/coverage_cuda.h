@@ -235,6 +235,16 @@ COV_API int64_t cov_get_trace(const cov_handle *h, double *ms, int64_t cap);
 /* Device time of the last cov_eval_batch* coverage-kernel launch(es) in milliseconds, measured
  * with CUDA events on the handle's stream (synchronises). */
 COV_API int cov_last_kernel_ms(cov_handle *h, double *ms);
+/* Shape of the last coverage-kernel launch of this handle (diagnostics; which kernel COV_KERNEL_AUTO and
+ * COV_KERNEL_SPAN resolved to). COV_ERR_STATE before the first launch. */
+typedef struct cov_launch_info {
+    int32_t kernel;         /* cov_kernel: SPAN = small-swarm kernel, SPAN_GENERAL = CTA per candidate, BRUTE, EXACT */
+    int32_t grid, block;    /* CTAs, threads per CTA */
+    int32_t smem_bytes;     /* dynamic shared memory per CTA */
+    int32_t band_rows;      /* framebuffer rows per band (ny: a single band) */
+    int32_t planes_in_smem; /* 1: bit planes staged in shared memory */
+} cov_launch_info;
+COV_API int cov_last_launch(const cov_handle *h, cov_launch_info *out);
 /* Running totals over every coverage-kernel launch of this handle: summed device time (CUDA
  * events on the launching stream) and number of launches (synchronises). Both nullable. */
 COV_API int cov_kernel_time_total(cov_handle *h, double *ms, int64_t *launches);

@@ -30,6 +30,11 @@ class GridInfo(C.Structure):
                 ("n_classes", C.c_int64), ("area_exact", C.c_int32), ("planes_in_smem", C.c_int32)]
 
 
+class LaunchInfo(C.Structure):
+    _fields_ = [("kernel", C.c_int32), ("grid", C.c_int32), ("block", C.c_int32), ("smem_bytes", C.c_int32),
+                ("band_rows", C.c_int32), ("planes_in_smem", C.c_int32)]
+
+
 class Limits(C.Structure):
     _fields_ = [("max_uavs", C.c_int64), ("max_nx", C.c_int64), ("max_ny", C.c_int64),
                 ("max_planes", C.c_int64), ("max_classes", C.c_int64)]
@@ -80,6 +85,7 @@ SIGNATURES = {
     "cov_get_trace": (_i64, [_vp, _pd, _i64]),
     "cov_last_kernel_ms": (_i, [_vp, _pd]),
     "cov_kernel_time_total": (_i, [_vp, _pd, _pi64]),
+    "cov_last_launch": (_i, [_vp, C.POINTER(LaunchInfo)]),
     "cov_generate_candidates": (_i, [_vp, _vp, _i64, _i64, C.c_uint64, _i64, _d, _d, _d, _d, _d]),
     "cov_multi_create": (_i, [C.POINTER(C.c_int), _i, C.POINTER(_vp)]),
     "cov_multi_destroy": (None, [_vp]),

@@ -1674,6 +1674,19 @@ extern "C" int cov_last_kernel_ms(cov_handle *h, double *ms)
     return COV_OK;
 }
 
+extern "C" int cov_last_launch(const cov_handle *h, cov_launch_info *out)
+{
+    if (!h || !out) return COV_ERR_INVALID;
+    if (h->last_info.block == 0) return COV_ERR_STATE;
+    out->kernel = h->last_info.kernel;
+    out->grid = h->last_info.grid;
+    out->block = h->last_info.block;
+    out->smem_bytes = h->last_info.smem_bytes;
+    out->band_rows = h->last_info.band_rows;
+    out->planes_in_smem = h->last_info.planes_in_smem;
+    return COV_OK;
+}
+
 extern "C" int cov_kernel_time_total(cov_handle *h, double *ms, int64_t *launches)
 {
     if (!h) return fail(nullptr, COV_ERR_INVALID, "NULL handle");

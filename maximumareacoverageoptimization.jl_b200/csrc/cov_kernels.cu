@@ -413,6 +413,7 @@ cudaError_t launch_eval(const GridDesc &g, const ObjParams &o, const LaunchCfg &
         li.grid = grid;
         li.block = warps * 32;
         li.smem_bytes = smem;
+        li.kernel = COV_KERNEL_EXACT;
         if (info) *info = li;
         return cudaGetLastError();
     }
@@ -434,6 +435,7 @@ cudaError_t launch_eval(const GridDesc &g, const ObjParams &o, const LaunchCfg &
         li.block = warps * 32;
         li.smem_bytes = smem;
         li.planes_in_smem = planes_smem;
+        li.kernel = COV_KERNEL_BRUTE;
         if (info) *info = li;
 #define COV_LAUNCH_BRUTE(M, S)                                                                      \
     do {                                                                                            \

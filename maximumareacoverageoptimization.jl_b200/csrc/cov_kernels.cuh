@@ -19,6 +19,7 @@ struct LaunchCfg {
 
 struct LaunchInfo {
     int grid, block, smem_bytes, band_rows, planes_in_smem;
+    int kernel; // cov_kernel of the kernel that ran (SPAN = small-swarm, SPAN_GENERAL = CTA per candidate)
 };
 
 // Coverage objective over B candidates (device pointers). counter: one ZEROED unsigned long long

@@ -334,6 +334,7 @@ cudaError_t launch_span_cta(const GridDesc &g, const ObjParams &o, const LaunchC
         info->smem_bytes = p.total_bytes;
         info->band_rows = p.band_rows;
         info->planes_in_smem = mode == kPlanesStaged;
+        info->kernel = COV_KERNEL_SPAN_GENERAL;
     }
     cudaError_t err;
 #define COV_LAUNCH_CTA(M, E)                                                                                      \

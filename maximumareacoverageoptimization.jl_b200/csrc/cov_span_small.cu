@@ -427,6 +427,7 @@ cudaError_t launch_span_small(const GridDesc &g, const ObjParams &o, const Launc
         info->smem_bytes = smem;
         info->band_rows = g.ny;
         info->planes_in_smem = 1;
+        info->kernel = COV_KERNEL_SPAN;
     }
 #define COV_SMALL_CASE(M, C)                                                                                     \
     case C:                                                                                                      \

@@ -310,6 +310,13 @@ class CoverageEngine:
         self._check(lib.cov_last_kernel_ms(self._h, C.byref(v)))
         return v.value
 
+    def last_launch(self) -> dict:
+        """Shape of the last coverage-kernel launch: kernel (KERNEL_SPAN = small-swarm kernel,
+        KERNEL_SPAN_GENERAL = CTA per candidate, ...), grid, block, smem_bytes, band_rows, planes_in_smem."""
+        li = _lib.LaunchInfo()
+        self._check(lib.cov_last_launch(self._h, C.byref(li)))
+        return {f: getattr(li, f) for f, _ in _lib.LaunchInfo._fields_}
+
     def trace(self) -> np.ndarray:
         """Timeline of the last host-path call under OPT_TRACE: (slices, 4) ms [h2d done, k start, k end, d2h done]."""
         n = lib.cov_get_trace(self._h, None, 0)

@@ -544,6 +544,9 @@ def test_full_c2_properties(cov, orc, engine):
     engine.set_params(N, r_max)
     X = cov.synth.random_candidates(B, N, seed=1)
     a = engine.eval_batch(X)
+    ll = engine.last_launch()
+    # (the last launch of a host-path call is its short tail slice: at most one persistent CTA per SM)
+    assert ll["kernel"] == cov.KERNEL_SPAN and ll["planes_in_smem"] == 1 and 1 <= ll["grid"] <= 148
     perm = np.array([3, 0, 4, 1, 2])
     Xp = np.concatenate([X[:, perm], X[:, N + perm], X[:, 2 * N + perm]], axis=1)
     b = engine.eval_batch(Xp)
@@ -797,6 +800,7 @@ def test_swarm_sizes_cta_kernel_vs_oracle(cov, orc, engine, fire_rows, N):
     engine.set_points(allp, 100, 100, 5.0, 5.0)
     engine.set_params(N, r_max, sep_min=15.0)
     check_against_oracle(cov, orc, engine, X, N, r_max, allp, sep_min=15.0)
+    assert engine.last_launch()["kernel"] == cov.KERNEL_SPAN_GENERAL
     pts = orc.createPOI(5.0, 5.0, 100.0, 100.0)
     engine.set_grid_full(100, 100, 5.0, 5.0)
     engine.set_params(N, r_max, sep_min=15.0)
@@ -882,3 +886,37 @@ def test_c3_c4_span_vs_brute_at_scale(cov, engine, n, N, B):
     assert np.array_equal(outs["span"][0], outs["brute"][0])
     assert np.array_equal(outs["span"][2], outs["brute"][2])
     assert outs["span"][1].min() > 0
+
+
+@pytest.mark.parametrize("nx,ny", [(32, 4095), (96, 2048)])
+def test_small_kernel_item_index_limits(cov, engine, nx, ny):
+    """The small-swarm kernel packs the per-disc item prefixes of a candidate into 16-bit fields and finds
+    the disc of an item with one packed compare.  Push the fields to their limits: 8 discs that each cover
+    every row of the tallest grid the kernel takes (8 x 4095 = 32 760 items, just below 0x7fff), discs
+    with no rows at all in between (equal prefixes), and mixtures; against the exact kernel."""
+    rng = np.random.default_rng(nx + ny)
+    fire = rng.random((nx, ny)) < 0.4
+    dx = dy = 1.0
+    engine.set_grid_bits(cov.synth.pack_bits(fire), nx, ny, dx, dy)
+    N, B = 8, 600
+    ex, ey = nx * dx, ny * dy
+    X = np.empty((B, 3 * N))
+    X[:, :N] = rng.random((B, N)) * ex
+    X[:, N:2 * N] = rng.random((B, N)) * ey
+    X[:, 2 * N:] = rng.random((B, N)) * 40.0
+    X[:200, N:2 * N] = ey / 2 + rng.random((200, N))          # every disc covers every row ...
+    X[:200, 2 * N:] = ey * (0.6 + rng.random((200, N)))       # ... of the grid: the largest item count
+    far = rng.random((B, N)) < 0.3                            # discs with no row on the grid
+    far[:100] = False
+    X[:, N:2 * N][far] = -1e6
+    X[300:330, 2 * N:] = 0.0                                  # all-empty candidates
+    engine.set_params(N, np.full(N, 10.0))
+    engine.set_option(cov.OPT_KERNEL, KERNELS["exact"])
+    want = engine.eval_batch(X)
+    assert engine.last_launch()["kernel"] == cov.KERNEL_EXACT
+    engine.set_option(cov.OPT_KERNEL, KERNELS["span"])
+    got = engine.eval_batch(X)
+    assert engine.last_launch()["kernel"] == cov.KERNEL_SPAN       # the small-swarm kernel took it
+    assert np.array_equal(got["count"], want["count"]), np.flatnonzero(got["count"] != want["count"])[:5]
+    assert np.array_equal(got["obj"].view(np.uint64), want["obj"].view(np.uint64))
+    assert want["count"][:100].min() == int(fire.sum())       # the full-cover candidates count every fire cell
