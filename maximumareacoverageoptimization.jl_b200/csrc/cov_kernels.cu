@@ -455,8 +455,13 @@ cudaError_t launch_eval(const GridDesc &g, const ObjParams &o, const LaunchCfg &
         return cudaGetLastError();
     }
     // span kernels: the small-swarm variant when it applies, else one CTA per candidate
-    if (cfg.kernel != COV_KERNEL_SPAN_GENERAL && span_small_applies(g, N, cfg, B, nullptr, nullptr))
-        return launch_span_small(g, o, cfg, dX, B, out, counter, stream, info);
+    bool small = cfg.kernel != COV_KERNEL_SPAN_GENERAL && span_small_applies(g, N, cfg, B, nullptr, nullptr);
+    // AUTO: a batch of up to a few thousand candidates finishes sooner with one CTA per candidate (10.5 us up
+    // to 444 candidates, +3.5 us per further 444) than with the warp-per-unit kernel, whose shortest launch is
+    // one 8-candidate unit per warp (21-57 us); measured crossover on B200 ~3 500 candidates for 5 UAVs,
+    // ~6 000 for 8 (tools/small_batch_routing.py).  COV_KERNEL_SPAN keeps the small-swarm kernel from 128 on.
+    if (small && cfg.kernel == COV_KERNEL_AUTO && B < 512ll * N + 1024) small = false;
+    if (small) return launch_span_small(g, o, cfg, dX, B, out, counter, stream, info);
     return launch_span_cta(g, o, cfg, dX, B, out, counter, stream, info);
 }
 
