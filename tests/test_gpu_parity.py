@@ -920,3 +920,23 @@ def test_small_kernel_item_index_limits(cov, engine, nx, ny):
     assert np.array_equal(got["count"], want["count"]), np.flatnonzero(got["count"] != want["count"])[:5]
     assert np.array_equal(got["obj"].view(np.uint64), want["obj"].view(np.uint64))
     assert want["count"][:100].min() == int(fire.sum())       # the full-cover candidates count every fire cell
+
+
+def test_auto_routing_by_batch_size(cov, orc, engine):
+    """COV_KERNEL_AUTO: poll-sized and mid-sized batches of a small swarm go to the CTA-per-candidate kernel
+    (lower latency), large ones to the small-swarm kernel; the results do not depend on the route."""
+    pts = orc.createPOI(5.0, 5.0, 100.0, 100.0)
+    engine.set_grid_full(100, 100, 5.0, 5.0)
+    N = 5
+    r_max = np.full(N, 30 * T)
+    engine.set_params(N, r_max, sep_min=15.0)
+    engine.set_option(cov.OPT_KERNEL, cov.KERNEL_AUTO)
+    X = rand_candidates(np.random.default_rng(11), 6000, N)
+    want = orc.eval_batch(X, N, r_max, pts, sep_min=15.0)
+    for B, kernel in ((1, cov.KERNEL_SPAN_GENERAL), (30, cov.KERNEL_SPAN_GENERAL), (200, cov.KERNEL_SPAN_GENERAL),
+                      (3000, cov.KERNEL_SPAN_GENERAL), (6000, cov.KERNEL_SPAN)):
+        got = engine.eval_batch(X[:B])
+        assert engine.last_launch()["kernel"] == kernel, (B, engine.last_launch())
+        assert np.array_equal(got["count"], want["count"][:B]) and np.array_equal(got["feasible"], want["feasible"][:B])
+        assert np.array_equal(got["obj"].view(np.uint64), want["obj"][:B].view(np.uint64))
+    assert engine.eval_one(X[5]) == want["obj"][5]
