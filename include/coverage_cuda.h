@@ -214,7 +214,7 @@ COV_API int cov_covered_mask(cov_handle *h, const double *x, uint8_t *mask);
  *      boundary integration in FP64 (Green's theorem; the reference ships only the pair primitives,
  *      src/Base_Functions.jl:230-355, and no driver, so this is an extension checked against closed forms and
  *      an independent restatement to 1e-9 relative, far inside north_star's 1e-5). No grid is involved.
- *      N <= 64. Host buffers, synchronous. */
+ *      N <= 1024 (one warp per candidate up to 64 discs, one CTA per candidate above). Host buffers, synchronous. */
 COV_API int cov_union_area_batch(cov_handle *h, const double *X, int64_t B, int64_t N, double *area);
 
 /* ---- streams, memory, timing (so hosts without a CUDA binding can keep data resident) ------ */

@@ -1600,7 +1600,7 @@ extern "C" int cov_union_area_batch(cov_handle *h, const double *X, int64_t B, i
 {
     if (!h) return fail(nullptr, COV_ERR_INVALID, "NULL handle");
     DeviceGuard dg(h->device);
-    if (N < 1 || N > 64) return fail(h, COV_ERR_LIMIT, "cov_union_area_batch: N must be 1..64");
+    if (N < 1 || N > kMaxUavs) return fail(h, COV_ERR_LIMIT, "cov_union_area_batch: N must be 1..1024");
     if (B < 0 || (B > 0 && (!X || !area))) return fail(h, COV_ERR_INVALID, "cov_union_area_batch: bad arguments");
     const size_t row_bytes = (size_t)3 * N * 8;
     const int64_t window = std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(B, 1), (int64_t)((256ull << 20) / row_bytes)));

@@ -564,9 +564,120 @@ __global__ void union_area_kernel(const double *__restrict__ X, long long B, int
         if (lane == 0) area[b] = mine;
     }
 }
+// Large swarms (64 < N <= kMaxUavs): one CTA per candidate, one warp per circle i, lanes over the other
+// circles j.  The covered angular intervals of circle i go to the warp's list in shared memory (warp-
+// aggregated appends); instead of sorting them, every interval END that no other interval covers opens an
+// exposed arc, which runs to the nearest interval START at or after it (plus the arc that starts at angle 0
+// when 0 is uncovered).  Among intervals with the same end the lowest list position speaks for all.  Same
+// formulas and tie rules as union_area_kernel; sums in a fixed order (deterministic).
+constexpr int kUnionBigWarps = 4;
+__global__ void __launch_bounds__(kUnionBigWarps * 32)
+union_area_big_kernel(const double *__restrict__ X, long long B, int N, double *__restrict__ area)
+{
+    extern __shared__ __align__(16) unsigned char union_smem[];
+    double *xs = reinterpret_cast<double *>(union_smem);                        // 3N staged doubles
+    double *lists = xs + 3 * N;                                                 // per warp: 2N starts, 2N ends
+    __shared__ double s_part[kUnionBigWarps];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double *ia = lists + (size_t)warp * 4 * N, *ib = ia + 2 * N;
+    const double two_pi = 6.283185307179586;
+    for (long long b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads(); // previous candidate retired
+        for (int t = tid; t < 3 * N; t += blockDim.x) xs[t] = __ldg(X + b * 3 * N + t);
+        __syncthreads();
+        double mine = 0.0; // lane-partial sum of this warp's circles
+        for (int i = warp; i < N; i += kUnionBigWarps) {
+            const double cxi = xs[i], cyi = xs[N + i], Ri = xs[2 * N + i];
+            if (!(Ri > 0.0)) continue; // warp-uniform
+            int n = 0;                 // list length, the same in every lane
+            bool whole = false;
+            for (int j0 = 0; j0 < N && !whole; j0 += 32) {
+                const int j = j0 + lane;
+                int k = 0; // intervals this lane appends (0, 1 or 2)
+                double a0 = 0, b0 = 0, a1 = 0, b1 = 0;
+                bool inside = false;
+                if (j < N && j != i) {
+                    const double Rj = xs[2 * N + j];
+                    if (Rj > 0.0) {
+                        const double dx = xs[j] - cxi, dy = xs[N + j] - cyi;
+                        const double d = hypot(dx, dy);
+                        if (d < Ri + Rj) {
+                            if (d + Ri <= Rj) {
+                                inside = !(d + Rj <= Ri && i < j); // identical discs: the lower index survives
+                            } else if (!(d + Rj <= Ri)) {
+                                const double phi = atan2(dy, dx);
+                                const double c = (Ri * Ri + d * d - Rj * Rj) / (2.0 * Ri * d);
+                                const double alpha = acos(fmax(-1.0, fmin(1.0, c)));
+                                double a = fmod(phi - alpha, two_pi);
+                                if (a < 0.0) a += two_pi;
+                                const double e = a + 2.0 * alpha;
+                                if (e > two_pi) {
+                                    a0 = a; b0 = two_pi; a1 = 0.0; b1 = e - two_pi; k = 2;
+                                } else {
+                                    a0 = a; b0 = e; k = 1;
+                                }
+                            }
+                        }
+                    }
+                }
+                whole = __any_sync(0xffffffffu, inside);
+                // exclusive prefix of k over the lanes: list positions in (j, first/second) order
+                int incl = k;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, off);
+                    if (lane >= off) incl += v;
+                }
+                const int at = n + incl - k;
+                if (k >= 1) { ia[at] = a0; ib[at] = b0; }
+                if (k == 2) { ia[at + 1] = a1; ib[at + 1] = b1; }
+                n += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (whole) continue;
+            __syncwarp();
+            // candidates for the start of an exposed arc: angle 0 (p == -1) and every interval end
+            double acc = 0.0;
+            for (int p = lane - 1; p < n; p += 32) {
+                const double pos = p < 0 ? 0.0 : ib[p];
+                bool covered = !(pos < two_pi);
+                double nxt = two_pi;
+                for (int q = 0; q < n && !covered; ++q) {
+                    const double aq = ia[q], bq = ib[q];
+                    if (q != p && aq <= pos && (pos < bq || (pos == bq && q < p))) covered = true;
+                    if (aq > pos && aq < nxt) nxt = aq; // (a start AT pos either covers it or is a zero-length interval)
+                }
+                if (!covered && nxt > pos) {
+                    double s1, c1, s2, c2;
+                    sincos(pos, &s1, &c1);
+                    sincos(nxt, &s2, &c2);
+                    acc += 0.5 * (Ri * Ri * (nxt - pos) + Ri * (cxi * (s2 - s1) - cyi * (c2 - c1)));
+                }
+            }
+            mine += acc;
+            __syncwarp(); // the list is rewritten for the warp's next circle
+        }
+        for (int off = 16; off; off >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, off);
+        if (lane == 0) s_part[warp] = mine;
+        __syncthreads();
+        if (tid == 0) {
+            double tot = 0.0;
+            for (int w = 0; w < kUnionBigWarps; ++w) tot += s_part[w];
+            area[b] = tot;
+        }
+    }
+}
+
 cudaError_t launch_union_area(const double *dX, long long B, int N, double *d_area, cudaStream_t s)
 {
     if (B <= 0) return cudaSuccess;
+    if (N > kUnionMaxN) {
+        const int smem = (3 * N + kUnionBigWarps * 4 * N) * 8;
+        cudaError_t err = cudaFuncSetAttribute(union_area_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (err != cudaSuccess) return err;
+        const int grid = (int)std::min<long long>(B, 148 * 4);
+        union_area_big_kernel<<<grid, kUnionBigWarps * 32, smem, s>>>(dX, B, N, d_area);
+        return cudaGetLastError();
+    }
     const int block = 128;
     const int grid = (int)std::min<long long>((B * 32 + block - 1) / block, 148 * 16);
     union_area_kernel<<<grid, block, 0, s>>>(dX, B, N, d_area);

@@ -669,9 +669,17 @@ def test_union_area_closed_forms_and_oracle(cov, npo, engine):
         got = float(engine.union_area(np.array([x], dtype=np.float64), n)[0])
         assert abs(got - want) <= UNION_RTOL * max(want, 1.0), (x, got, want)
         assert abs(npo.union_area(x) - want) <= 1e-12 * max(want, 1.0)
+        # the same case padded with zero-radius discs to 70 circles: the CTA-per-candidate kernel (N > 64)
+        pad = 70 - n
+        xp = np.concatenate([x[:n], np.zeros(pad), x[n:2 * n], np.zeros(pad), x[2 * n:], np.zeros(pad)])
+        got = float(engine.union_area(xp[None, :], 70)[0])
+        assert abs(got - want) <= UNION_RTOL * max(want, 1.0), ("padded", x, got, want)
+    same = np.concatenate([np.full(100, 3.0), np.full(100, 7.0), np.full(100, 2.0)])
+    assert abs(float(engine.union_area(same[None, :], 100)[0]) - 4 * math.pi) <= UNION_RTOL * 4 * math.pi  # 100 identical
     rng = np.random.default_rng(4)
-    for n in (1, 2, 5, 20, 64):
-        X = np.concatenate([rng.random((200, 2 * n)) * 120, 2 + rng.random((200, n)) * 30], axis=1)
+    for n in (1, 2, 5, 20, 64, 65, 200):
+        nb = 200 if n <= 64 else 40
+        X = np.concatenate([rng.random((nb, 2 * n)) * 120, 2 + rng.random((nb, n)) * 30], axis=1)
         X[:20, :2 * n] = 50 + X[:20, :2 * n] * 0.05  # tight clusters: containment and many crossings
         got = engine.union_area(X, n)
         want = np.array([npo.union_area(x) for x in X])
@@ -680,7 +688,11 @@ def test_union_area_closed_forms_and_oracle(cov, npo, engine):
         assert np.all(got >= math.pi * np.max(X[:, 2 * n:], axis=1) ** 2 * (1 - 1e-12))
     assert cov.AreaCoverageCalculation.unionArea(np.array([0, 1, 0, 0, 1, 1.0]), engine) == pytest.approx(lens(1.0), rel=1e-12)
     with pytest.raises(cov.CoverageError):
-        engine.union_area(np.zeros((1, 3 * 65)), 65)
+        engine.union_area(np.zeros((1, 3 * 1025)), 1025)
+    big = np.concatenate([rng.random((3, 2048)) * 500, 2 + rng.random((3, 1024)) * 20], axis=1)  # the library's maximum
+    got = engine.union_area(big, 1024)
+    want = np.array([npo.union_area(x) for x in big])
+    assert np.all(np.abs(got - want) <= UNION_RTOL * want)
 
 
 def test_union_area_vs_fine_grid_count(cov, orc, engine):
