@@ -56,6 +56,46 @@ function remove_covered!(h::Handle, xyR::Vector{Float64})
     return removed[]
 end
 
+"update_POI on the device-resident store (src/CellFunctions.jl:59-77): append list entries, duplicates add up."
+function add_points!(h::Handle, points::Vector{Vector{Float64}})
+    flat = Vector{Float64}(undef, 5 * length(points))
+    @inbounds for (p, pt) in enumerate(points), k in 1:5
+        flat[5 * (p - 1) + k] = pt[k]
+    end
+    GC.@preserve flat check(h, ccall((:cov_add_points, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64),
+        h.ptr, flat, length(points)))
+end
+
+"""
+    fire_init!(h, state; dx = 5.0, dy = 5.0, push_initial = true)
+    fire_step!(h, wind_speed, wind_direction, prob_spread; seed = 0, step = 0, append = true)
+
+The forest-fire automaton of src/DynamicArea.jl:17-86 on the device: `state` is the `nx x ny` `UInt8` grid
+(0 EMPTY, 1 TREE, 2 FIRE); every step pushes the newly ignited cells straight into the cell store that the
+objective reads (no xlsx hand-off). `fire_step!` returns the number of entries pushed.
+"""
+function fire_init!(h::Handle, state::Matrix{UInt8}; dx = 5.0, dy = 5.0, push_initial = true)
+    nx, ny = size(state)
+    GC.@preserve state check(h, ccall((:cov_fire_init, LIB), Cint,
+        (Ptr{Cvoid}, Int64, Int64, Float64, Float64, Ptr{UInt8}, Int32), h.ptr, nx, ny, dx, dy, state, push_initial ? 1 : 0))
+end
+function fire_step!(h::Handle, wind_speed, wind_direction, prob_spread; seed = 0, step = 0, append = true)
+    pushed = Ref{Int64}(0)
+    check(h, ccall((:cov_fire_step, LIB), Cint,
+        (Ptr{Cvoid}, Float64, Float64, Float64, UInt64, Int64, Int32, Ref{Int64}),
+        h.ptr, wind_speed, wind_direction, prob_spread, seed, step, append ? 1 : 0, pushed))
+    return pushed[]
+end
+
+"Exact area of the union of the discs of every column of `X` (3N x B, [x; y; R]); no grid involved."
+function union_area(h::Handle, X::Matrix{Float64})
+    N = size(X, 1) ÷ 3; B = size(X, 2)
+    area = Vector{Float64}(undef, B)
+    GC.@preserve X area check(h, ccall((:cov_union_area_batch, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Ptr{Float64}), h.ptr, X, B, N, area))
+    return area
+end
+
 "Captured variables of createObjective / create_cons3 / cons8 / cons7."
 function set_params!(h::Handle, N::Integer, r_max::Vector{Float64}; penalty = 1e5,
                      prev::Union{Nothing,Vector{Float64}} = nothing, d_lim::Vector{Float64} = fill(10.0, N),
