@@ -8,18 +8,17 @@
 //   * the CTA's 8 warps share ONE candidate: its 3N doubles are staged in shared memory, the disc
 //     records are built by all threads, the O(N^2) separation test is spread over the warps while one
 //     lane forms the order-dependent penalty sum;
-//   * the union framebuffer lives in shared memory as a BAND of grid rows (the whole grid when it
-//     fits: 1024 x 33 words = 132 KB; 427-row bands for 4096^2);
+//   * the union framebuffer lives in shared memory as a BAND of grid rows (268-row bands at 1024^2 and
+//     96-row bands at 4096^2 when the band's fire words are staged beside it);
 //   * per band the work is cut into units of 32 rows of one disc (a unit -> disc table built by a
 //     CTA-wide scan); warps take units in pairs from a shared-memory dispenser and every lane handles
-//     one row of each unit: two independent
-//     spans per lane, atomicOr into the band, popcount of the newly set bits against the fire
-//     plane, whose rows for the band are staged in shared memory by ONE TMA bulk copy per band
-//     (cp.async.bulk + mbarrier, issued while warp 0 builds the band's unit table); small swarms and
-//     multi-plane stores read the fire words through L1/L2 instead.
+//     one row of each unit: two independent spans per lane, atomicOr into the band, popcount of the
+//     newly set bits against the fire plane, whose rows for the band are staged in shared memory by ONE
+//     TMA bulk copy per band (cp.async.bulk + mbarrier, issued while the CTA builds the band's unit
+//     table); small swarms and multi-plane stores read the fire words through L1/L2 instead.
 // Persistent grid, up to three 256-thread CTAs per SM so that one candidate's serial phases
-// (dispense, stage, setup, barriers) overlap another's span work; candidates come from an atomic
-// counter.
+// (stage, setup, barriers) overlap another's span work; a CTA's first candidate is its block index,
+// further ones come from an atomic counter (a poll set, one candidate per CTA, never touches it).
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdint>
