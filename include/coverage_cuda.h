@@ -55,7 +55,7 @@ typedef enum cov_status {
 /* Kernel selection for cov_set_option(COV_OPT_KERNEL). */
 enum {
     COV_KERNEL_AUTO = 0,    /* row-span kernels (default): the small-swarm variant (N <= 8, framebuffer in shared
-                               memory) for batches of a few thousand candidates and more, else the general one */
+                               memory) for batches of a thousand or two candidates and more, else the general one */
     COV_KERNEL_SPAN = 1,    /* row-span kernels, small-swarm variant whenever it applies (from 128 candidates on) */
     COV_KERNEL_BRUTE = 2,   /* every cell against every disc, FP32 band + FP64 exact band cells */
     COV_KERNEL_EXACT = 3,   /* every cell against every disc in FP64 only (slow cross-check) */

@@ -456,11 +456,12 @@ cudaError_t launch_eval(const GridDesc &g, const ObjParams &o, const LaunchCfg &
     }
     // span kernels: the small-swarm variant when it applies, else one CTA per candidate
     bool small = cfg.kernel != COV_KERNEL_SPAN_GENERAL && span_small_applies(g, N, cfg, B, nullptr, nullptr);
-    // AUTO: a batch of up to a few thousand candidates finishes sooner with one CTA per candidate (10.5 us up
-    // to 444 candidates, +3.5 us per further 444) than with the warp-per-unit kernel, whose shortest launch is
-    // one 8-candidate unit per warp (21-57 us); measured crossover on B200 ~3 500 candidates for 5 UAVs,
-    // ~6 000 for 8 (tools/small_batch_routing.py).  COV_KERNEL_SPAN keeps the small-swarm kernel from 128 on.
-    if (small && cfg.kernel == COV_KERNEL_AUTO && B < 512ll * N + 1024) small = false;
+    // AUTO: a batch of up to one or two thousand candidates finishes sooner with one CTA per candidate (9 us
+    // up to 444 candidates, +3.5 us per further 444) than with the warp-per-unit kernel, whose shortest launch
+    // (every warp one 4-candidate unit, spread over all SMs) lasts 17-21 us for 5 UAVs and 23-27 us for 8;
+    // measured crossover on B200 1 100 - 1 700 candidates for 5 UAVs, 2 000 - 2 300 for 8
+    // (tools/small_batch_routing.py).  COV_KERNEL_SPAN keeps the small-swarm kernel from 128 on.
+    if (small && cfg.kernel == COV_KERNEL_AUTO && B < 128ll * N + 768) small = false;
     if (small) return launch_span_small(g, o, cfg, dX, B, out, counter, stream, info);
     return launch_span_cta(g, o, cfg, dX, B, out, counter, stream, info);
 }

@@ -102,17 +102,22 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
     ictx.N = N;
     ictx.force_exact = force_exact;
 
-    // units are taken one ahead: while unit u is processed the candidates of unit u+1 are already on
-    // their way into L2
-    unsigned long long next = 0;
-    if (lane == 0) next = atomicAdd(counter, 1ull);
-    next = __shfl_sync(0xffffffffu, next, 0);
+    // units: the first one of a warp is static (warp w of CTA c takes unit c + gridDim.x * w, so a batch of
+    // fewer units than warps spreads over all SMs and nobody holds two while another has none); further
+    // units come from the global dispenser and are taken one ahead: while unit u is processed the
+    // candidates of unit u+1 are already on their way into L2
+    const unsigned long long total_warps = (unsigned long long)gridDim.x * (unsigned long long)warps;
+    const bool dynamic_units = (unsigned long long)n_chunks > total_warps; // uniform over the grid
+    unsigned long long next = (unsigned long long)blockIdx.x + (unsigned long long)gridDim.x * (unsigned long long)warp;
     const bool x_aligned = (reinterpret_cast<unsigned long long>(X) & 15ull) == 0;
     for (;;) {
         const unsigned long long chunk = next;
         if ((long long)chunk >= n_chunks) break;
-        if (lane == 0) next = atomicAdd(counter, 1ull);
-        next = __shfl_sync(0xffffffffu, next, 0);
+        next = (unsigned long long)n_chunks;
+        if (dynamic_units) {
+            if (lane == 0) next = total_warps + atomicAdd(counter, 1ull);
+            next = __shfl_sync(0xffffffffu, next, 0);
+        }
         const long long base = (long long)chunk * CHUNK;
         const int in_chunk = (int)min((long long)CHUNK, B - base);
         if ((long long)next < n_chunks) {
@@ -420,7 +425,9 @@ cudaError_t launch_span_small(const GridDesc &g, const ObjParams &o, const Launc
     const bool multi = !(g.n_planes == 1 && g.n_classes == 1 && g.plane_mult[0] == 1);
     const int smem = g.n_planes * g.plane_words * 4 + small_param_bytes(o.N) + warps * small_warp_bytes(g, o.N, chunk) + 16;
     const long long chunks = (B + chunk - 1) / chunk;
-    const int grid = (int)std::min<long long>((chunks + warps - 1) / warps, (long long)cfg.num_sms);
+    // a batch of fewer units than warps is spread over all SMs with fewer warps each (they run faster alone)
+    const int grid = (int)std::min<long long>(chunks, (long long)cfg.num_sms);
+    warps = (int)std::min<long long>(warps, (chunks + grid - 1) / grid);
     if (info) {
         info->grid = grid;
         info->block = warps * 32;

@@ -946,7 +946,7 @@ def test_auto_routing_by_batch_size(cov, orc, engine):
     X = rand_candidates(np.random.default_rng(11), 6000, N)
     want = orc.eval_batch(X, N, r_max, pts, sep_min=15.0)
     for B, kernel in ((1, cov.KERNEL_SPAN_GENERAL), (30, cov.KERNEL_SPAN_GENERAL), (200, cov.KERNEL_SPAN_GENERAL),
-                      (3000, cov.KERNEL_SPAN_GENERAL), (6000, cov.KERNEL_SPAN)):
+                      (1000, cov.KERNEL_SPAN_GENERAL), (3000, cov.KERNEL_SPAN), (6000, cov.KERNEL_SPAN)):
         got = engine.eval_batch(X[:B])
         assert engine.last_launch()["kernel"] == kernel, (B, engine.last_launch())
         assert np.array_equal(got["count"], want["count"][:B]) and np.array_equal(got["feasible"], want["feasible"][:B])
