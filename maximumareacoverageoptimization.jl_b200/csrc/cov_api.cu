@@ -1088,6 +1088,12 @@ static void host_copy(cov_handle *h, void *dst, const void *src, size_t bytes)
 #ifndef COV_ZC_IN_LIMIT
 #define COV_ZC_IN_LIMIT (256u << 10) // the whole small-batch path; measured against 32 KiB: 512 candidates 53 -> 42 us, 2184 candidates 74 -> 62 us
 #endif
+#ifndef COV_ZC_MID_LIMIT
+// measured on B200 (5 UAVs, pinned buffers, tools/batch_size_sweep.py): 4096 candidates 70 -> 55 us, 32 768 168 -> 133 us,
+// 131 072 465 -> 392 us, 262 144 761 -> 715 us; level with the copy-engine pipeline at 524 288 (SM reads reach
+// ~49 GB/s over PCIe, the DMA engine 55 GB/s), behind it at 1 M
+#define COV_ZC_MID_LIMIT (48u << 20)
+#endif
 static int eval_host_small(cov_handle *h, const double *X, int64_t B, double *obj, int64_t *count, uint8_t *feasible,
                            int64_t *class_count, double *progressive)
 {
@@ -1166,6 +1172,27 @@ static int eval_host(cov_handle *h, const double *X, int64_t B, double *obj, int
     const size_t row_bytes = (size_t)3 * N * 8;
     if ((size_t)B * row_bytes <= (256u << 10) && (size_t)B * (25 + 8 * (size_t)ncls) <= (1536u << 10) && h->chunk == 0)
         return eval_host_small(h, X, B, obj, count, feasible, class_count, progressive);
+#if COV_ZC_MID_LIMIT > 0
+    // mid-size batches in pinned buffers: one launch that reads the candidates straight over PCIe (the
+    // kernel's own unit prefetch overlaps transfer and compute) and writes the results back the same way
+    if (h->zero_copy_out && h->chunk == 0 && N <= 8 && (size_t)B * row_bytes <= (size_t)(COV_ZC_MID_LIMIT) && is_pinned_host(X) &&
+        is_pinned_host(obj) && (!count || is_pinned_host(count)) && (!feasible || is_pinned_host(feasible)) &&
+        (!class_count || is_pinned_host(class_count)) && (!progressive || is_pinned_host(progressive))) {
+        const double *vx = (const double *)device_view((void *)X);
+        EvalOut out{};
+        out.obj = (double *)device_view(obj);
+        out.count = count ? (long long *)device_view(count) : nullptr;
+        out.feasible = feasible ? (unsigned char *)device_view(feasible) : nullptr;
+        out.class_count = class_count ? (long long *)device_view(class_count) : nullptr;
+        out.progressive = progressive ? (double *)device_view(progressive) : nullptr;
+        if (vx && out.obj && (!count || out.count) && (!feasible || out.feasible) && (!class_count || out.class_count) &&
+            (!progressive || out.progressive)) {
+            OK(launch_on_main(h, vx, B, out, true));
+            CK(cudaStreamSynchronize(h->stream));
+            return COV_OK;
+        }
+    }
+#endif
     // device window: at most ~1 GiB of candidates at a time
     const int64_t window = std::max<int64_t>(1, std::min<int64_t>(B, (int64_t)((1ull << 30) / row_bytes)));
     // slice size: ~16 MiB of candidates, a multiple of 32 candidates (keeps device slices 16-byte aligned)
