@@ -488,9 +488,22 @@ def test_host_pipeline_chunks_and_pinned(cov, orc, engine):
     Xp = engine.pinned((B, 3 * N))
     Xp[:] = X
     out = {"obj": engine.pinned((B,)), "count": engine.pinned((B,), np.int64), "feasible": engine.pinned((B,), np.uint8)}
-    r = engine.eval_batch(Xp, out=out)
+    r = engine.eval_batch(Xp, out=out)           # pinned buffers through the slice pipeline (OPT_CHUNK still set)
     for k in ("obj", "count", "feasible"):
         assert np.array_equal(r[k], base[k])
+    engine.set_option(cov.OPT_CHUNK, 0)
+    for zc in (1, 0):                              # one zero-copy launch on the caller's buffers / copy engines
+        engine.set_option(cov.OPT_ZEROCOPY_OUT, zc)
+        for k in out:
+            out[k][:] = 0
+        r = engine.eval_batch(Xp, out=out)
+        for k in ("obj", "count", "feasible"):
+            assert np.array_equal(r[k], base[k]), (zc, k)
+        for nb in (1, 30, 700, 2184):              # the small-batch path: pinned scratch, zero-copy or copied
+            r = engine.eval_batch(X[:nb])
+            for k in ("obj", "count", "feasible"):
+                assert np.array_equal(r[k], base[k][:nb]), (zc, nb, k)
+    engine.set_option(cov.OPT_ZEROCOPY_OUT, 1)
     sample = orc.eval_batch(X[:300], N, r_max, orc.createPOI(5.0, 5.0, 100.0, 100.0))
     assert np.array_equal(base["obj"][:300], sample["obj"])
 
