@@ -6,7 +6,10 @@
 // on the CPU: without a CUDA device every entry point that needs one fails with COV_ERR_CUDA.
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -38,7 +41,7 @@ public:
     {
         {
             std::lock_guard<std::mutex> lk(m_);
-            stop_ = true;
+            stop_.store(true);
         }
         cv_.notify_all();
         for (auto &t : workers_) t.join();
@@ -52,6 +55,7 @@ public:
             return;
         }
         const size_t per = ((bytes + parts - 1) / parts + 4095) / 4096 * 4096;
+        int posted = 0;
         {
             std::lock_guard<std::mutex> lk(m_);
             for (size_t k = 1; k < parts; ++k) {
@@ -59,40 +63,66 @@ public:
                 if (off >= bytes) break;
                 const size_t n = std::min(per, bytes - off);
                 tasks_.push_back([=] { memcpy((char *)dst + off, (const char *)src + off, n); });
-                ++pending_;
+                ++posted;
             }
+            pending_.fetch_add(posted);
+            avail_.fetch_add(posted);
         }
         cv_.notify_all();
         memcpy(dst, src, std::min(per, bytes));
-        std::unique_lock<std::mutex> lk(m_);
-        done_.wait(lk, [this] { return pending_ == 0; });
+        // the parts are short (a few hundred microseconds at most): wait for them without sleeping
+        for (unsigned spins = 0; pending_.load(std::memory_order_acquire) != 0; ++spins) {
+            if ((spins & 1023u) == 1023u) std::this_thread::yield();
+            else relax();
+        }
     }
 
 private:
+    static void relax()
+    {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#else
+        std::this_thread::yield();
+#endif
+    }
+    // Workers stay awake for about a millisecond after their last job: the slices of one pipelined call arrive
+    // every few hundred microseconds, and a futex wake-up per slice cost more than the copy itself.
     void run()
     {
         for (;;) {
+            const auto idle_since = std::chrono::steady_clock::now();
+            unsigned spins = 0;
+            while (avail_.load(std::memory_order_acquire) == 0 && !stop_.load(std::memory_order_relaxed)) {
+                relax();
+                if ((++spins & 255u) == 0 &&
+                    std::chrono::steady_clock::now() - idle_since > std::chrono::microseconds(1000)) {
+                    std::unique_lock<std::mutex> lk(m_);
+                    cv_.wait(lk, [this] { return stop_.load() || avail_.load() > 0; });
+                    break;
+                }
+            }
             std::function<void()> job;
             {
-                std::unique_lock<std::mutex> lk(m_);
-                cv_.wait(lk, [this] { return stop_ || !tasks_.empty(); });
-                if (stop_ && tasks_.empty()) return;
+                std::lock_guard<std::mutex> lk(m_);
+                if (tasks_.empty()) {
+                    if (stop_.load()) return;
+                    continue;
+                }
                 job = std::move(tasks_.back());
                 tasks_.pop_back();
+                avail_.fetch_sub(1);
             }
             job();
-            {
-                std::lock_guard<std::mutex> lk(m_);
-                if (--pending_ == 0) done_.notify_all();
-            }
+            pending_.fetch_sub(1, std::memory_order_release);
         }
     }
     std::vector<std::thread> workers_;
     std::vector<std::function<void()>> tasks_;
     std::mutex m_;
-    std::condition_variable cv_, done_;
-    int pending_ = 0;
-    bool stop_ = false;
+    std::condition_variable cv_;
+    std::atomic<int> pending_{0}, avail_{0};
+    std::atomic<bool> stop_{false};
 };
 
 // ------------------------------------------------------------------------------------------
@@ -1073,10 +1103,16 @@ extern "C" int cov_eval_batch_device(cov_handle *h, const double *dX, int64_t B,
 // Pageable host buffers go through two pinned staging buffers; pinned ones are DMA'd in place.
 static void host_copy(cov_handle *h, void *dst, const void *src, size_t bytes)
 {
-    if (bytes >= (4u << 20)) {
+    static const size_t pool_min = [] {
+        const char *e = getenv("COV_POOL_MIN_BYTES"); // experiments; default: from 1 MiB on
+        return e ? (size_t)strtoull(e, nullptr, 10) : (size_t)(1u << 20);
+    }();
+    if (bytes >= pool_min) {
         if (!h->pool) {
             const unsigned hc = std::thread::hardware_concurrency();
-            h->pool = new CopyPool((int)std::min(7u, std::max(2u, hc / 2) - 1u)); // + the calling thread
+            const char *e = getenv("COV_POOL_THREADS"); // experiments; default: up to 7 workers + the calling thread
+            const unsigned want = e ? (unsigned)atoi(e) : 7u;
+            h->pool = new CopyPool((int)std::min(std::max(want, 1u), std::max(2u, hc) - 1u));
         }
         h->pool->copy(dst, src, bytes);
     } else {
