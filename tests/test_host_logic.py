@@ -75,3 +75,18 @@ def test_candidates_shapes(cov):
     P = cov.synth.philox_candidates(64, 3, seed=99, first_index=1 << 33)
     assert P.shape == (64, 9) and len(np.unique(P)) == P.size
     assert np.array_equal(P[10:20], cov.synth.philox_candidates(10, 3, seed=99, first_index=(1 << 33) + 10))
+
+
+def test_every_python_file_compiles():
+    """tools/, the package, bench.py and __graft_entry__.py are syntactically valid (the GPU-side tools are not
+    exercised by the CPU suite otherwise)."""
+    import glob
+    import os
+    import py_compile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = glob.glob(os.path.join(root, "tools", "*.py")) + glob.glob(os.path.join(root, "oracle", "*.py")) + \
+        glob.glob(os.path.join(root, "maximumareacoverageoptimization.jl_b200", "*.py")) + \
+        [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py"), os.path.join(root, "coverage_b200.py")]
+    assert len(files) > 30
+    for f in files:
+        py_compile.compile(f, doraise=True, cfile=os.devnull)
