@@ -82,11 +82,11 @@ def test_every_python_file_compiles():
     exercised by the CPU suite otherwise)."""
     import glob
     import os
-    import py_compile
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     files = glob.glob(os.path.join(root, "tools", "*.py")) + glob.glob(os.path.join(root, "oracle", "*.py")) + \
         glob.glob(os.path.join(root, "maximumareacoverageoptimization.jl_b200", "*.py")) + \
         [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py"), os.path.join(root, "coverage_b200.py")]
     assert len(files) > 30
     for f in files:
-        py_compile.compile(f, doraise=True, cfile=os.devnull)
+        with open(f) as fh:
+            compile(fh.read(), f, "exec")
