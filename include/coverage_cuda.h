@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define COV_ABI_VERSION 1
+#define COV_ABI_VERSION 2 /* 2: COV_OPT_PROGRESSIVE_INDEX, cov_get_class_weights, cov_eval_area_ordered */
 
 #if defined(__GNUC__)
 #define COV_API __attribute__((visibility("default")))
@@ -73,9 +73,13 @@ enum {
     COV_OPT_PLANE_MODE = 9,     /* CTA kernel, how fire words are read: -1 auto (default), 0 through L2 only when
                                    the framebuffer atomic left new bits, 1 through L2 ahead of the atomics,
                                    2 staged in shared memory band by band with TMA bulk copies */
-    COV_OPT_ZEROCOPY_OUT = 8    /* 1 (default): the host path's kernels write their results straight into pinned host
+    COV_OPT_ZEROCOPY_OUT = 8,   /* 1 (default): the host path's kernels write their results straight into pinned host
                                    memory; 0: into device buffers, copied back slice by slice */
-    
+    COV_OPT_PROGRESSIVE_INDEX = 10 /* which progressive constraint the `progressive` output of cov_eval_batch_ex is:
+                                   0 (default) cons1_progressive = sum over every UAV of max(R_i - r_max_i, 0.0)
+                                   (src/TDM_Constraints.jl:182-195); k >= 1 the single-UAV forms, 1-based index as in
+                                   the reference: 2 = cons2_progressive (:197-208), 3 = cons3_progressive (:210-221).
+                                   k > N is rejected by the evaluation calls with COV_ERR_INVALID */
 };
 
 typedef struct cov_handle cov_handle;
@@ -120,7 +124,9 @@ COV_API int cov_set_points(cov_handle *h, const double *pts5, int64_t P, int64_t
 COV_API int cov_set_grid_full(cov_handle *h, int64_t nx, int64_t ny, double dx, double dy);
 
 /* Append list entries (update_POI, src/CellFunctions.jl:59-79): same rules as cov_set_points,
- * multiplicities add up. */
+ * multiplicities add up. Limits of the store (also of cov_set_points): at most 4 distinct weights (weight classes),
+ * one weight per cell, at most 255 entries per cell (COV_ERR_LIMIT / COV_ERR_INVALID otherwise). A failing append
+ * leaves the store exactly as it was. */
 COV_API int cov_add_points(cov_handle *h, const double *pts5, int64_t P);
 
 typedef struct cov_grid_info {
@@ -135,6 +141,9 @@ typedef struct cov_grid_info {
     int32_t planes_in_smem; /* 1: the span kernel stages the planes in shared memory */
 } cov_grid_info;
 COV_API int cov_get_grid_info(const cov_handle *h, cov_grid_info *info);
+/* The weight of every class as the device numbers them (class k of `class_count`, the order fixed when the
+ * store was created; it does NOT follow later removals). Writes min(cap, n_classes) doubles. */
+COV_API int cov_get_class_weights(const cov_handle *h, double *class_weight, int64_t cap);
 /* Read the device-resident multiplicity plane back (nx*ny bytes). */
 COV_API int cov_get_grid_cells(cov_handle *h, uint8_t *mult);
 

@@ -151,7 +151,9 @@ class ResidentList:
         if info["area_exact"]:
             res = eng.eval_batch(circles.reshape(1, -1), want_feasible=False, want_class_count=True)
             cc = res["class_count"][0]
-            w = self.class_weights(info["n_classes"])
+            # the DEVICE's class numbering: fixed when the store was created, it does not follow removals
+            # (the host list's order of first appearance does)
+            w = eng.class_weights()
             area = 0.0
             for k in range(info["n_classes"]):
                 area += w[k] * float(cc[k])  # every term and partial sum exact (area_exact)
@@ -162,15 +164,6 @@ class ResidentList:
         w = self.points.data[covered, 3]
         area = float(np.cumsum(w)[-1]) if w.size else 0.0  # cumsum: strictly sequential
         return area, int(covered.sum())
-
-    def class_weights(self, n_classes: int):
-        """Distinct weights in order of first appearance (how cov_set_points numbers classes)."""
-        w = self.points.data[:, 3]
-        _, first = np.unique(w, return_index=True)
-        ws = [float(w[k]) for k in sorted(first)]
-        if not ws:
-            ws = [self.points.dx * self.points.dy]
-        return ws[:max(n_classes, 1)]
 
 
 _resident_cache: dict[int, ResidentList] = {}

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import numpy as np
 
+from ._lib import OPT_PROGRESSIVE_INDEX
 from .engine import CoverageEngine, TAN_HALF_FOV_DEFAULT
 
 
@@ -94,7 +95,27 @@ def create_cons8(N: int, sep: float = 15.0, device: int = 0):
     return c
 
 
+def _create_progressive(name: str, which: int, N: int, r_max, device: int):
+    r = np.ascontiguousarray(r_max, dtype=np.float64).ravel()
+    if which > N:
+        raise ValueError(f"{name} reads UAV {which} but the swarm has {N}")
+
+    def configure(e):
+        e.set_params(N, r, 0.0)
+        e.set_option(OPT_PROGRESSIVE_INDEX, which)
+    return _Constraint(name, N, configure, device, progressive=True)
+
+
 def create_cons1_progressive(N: int, r_max, device: int = 0):
     """src/TDM_Constraints.jl:182-195 -- sum_i max(R_i - r_max_i, 0.0)."""
-    r = np.ascontiguousarray(r_max, dtype=np.float64).ravel()
-    return _Constraint("cons1_progressive", N, lambda e: e.set_params(N, r, 0.0), device, progressive=True)
+    return _create_progressive("cons1_progressive", 0, N, r_max, device)
+
+
+def create_cons2_progressive(N: int, r_max, device: int = 0):
+    """src/TDM_Constraints.jl:197-208 -- max(R_2 - r_max_2, 0.0): the term of UAV i = 2 alone."""
+    return _create_progressive("cons2_progressive", 2, N, r_max, device)
+
+
+def create_cons3_progressive(N: int, r_max, device: int = 0):
+    """src/TDM_Constraints.jl:210-221 -- max(R_3 - r_max_3, 0.0): the term of UAV i = 3 alone."""
+    return _create_progressive("cons3_progressive", 3, N, r_max, device)

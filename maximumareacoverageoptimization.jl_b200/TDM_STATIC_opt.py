@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import numpy as np
 
+from . import _lib
 from .CellFunctions import Cells
 from .AreaCoverageCalculation import PointList, ResidentList
 
@@ -21,7 +22,6 @@ class AreaMaxObjective:
         self.N = int(N)
         self.r_max = r_max  # captured by reference, like the Julia closure
         self._fused = {}
-        self._param_key = None
 
     def _resident(self) -> ResidentList:
         c = self.cells
@@ -45,7 +45,6 @@ class AreaMaxObjective:
             else:
                 fused.update(f)
         self._fused = fused
-        self._param_key = None
         return rest
 
     def native_solver(self, constraints):
@@ -62,10 +61,13 @@ class AreaMaxObjective:
         res = self._resident()
         eng = res.sync()
         r = np.ascontiguousarray(self.r_max, dtype=np.float64).ravel()
-        key = (r.tobytes(), id(self._fused))
-        if self._param_key != key or eng.N != self.N:
+        # the engine is shared (other objectives on the same cells, calculateArea, constraints): the token of
+        # whoever configured it last lives on the engine and is cleared by every set_params()
+        key = (id(self), r.tobytes(), id(self._fused))
+        if eng.param_owner != key or eng.N != self.N:
             eng.set_params(self.N, r, 1e5, **self._fused)
-            self._param_key = key
+            eng.set_option(_lib.OPT_PROGRESSIVE_INDEX, 0)
+            eng.param_owner = key
         return res, eng
 
     def batch(self, X, want_feasible=False):
@@ -87,7 +89,6 @@ class AreaMaxObjective:
 
     def _replay(self, res, x):
         area, _ = res.area_and_count(x)
-        self._param_key = None  # area_and_count may have changed the engine's parameters
         violation = 0.0
         for i in range(self.N):
             violation += abs(float(x[i + 2 * self.N]) - float(self.r_max[i]))

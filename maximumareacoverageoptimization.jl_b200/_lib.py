@@ -22,6 +22,7 @@ COV_ERR_NOMEM = -6
 
 KERNEL_AUTO, KERNEL_SPAN, KERNEL_BRUTE, KERNEL_EXACT, KERNEL_SPAN_GENERAL = 0, 1, 2, 3, 4
 OPT_KERNEL, OPT_WARPS_PER_CTA, OPT_CTAS_PER_SM, OPT_BAND_ROWS, OPT_FORCE_EXACT, OPT_CHUNK, OPT_TRACE, OPT_ZEROCOPY_OUT, OPT_PLANE_MODE = 1, 2, 3, 4, 5, 6, 7, 8, 9
+OPT_PROGRESSIVE_INDEX = 10
 
 
 class GridInfo(C.Structure):
@@ -59,6 +60,7 @@ SIGNATURES = {
     "cov_add_points": (_i, [_vp, _vp, _i64]),
     "cov_get_grid_info": (_i, [_vp, C.POINTER(GridInfo)]),
     "cov_get_grid_cells": (_i, [_vp, _vp]),
+    "cov_get_class_weights": (_i, [_vp, _pd, _i64]),
     "cov_remove_covered": (_i, [_vp, _vp, _i64, _pi64]),
     "cov_fire_init": (_i, [_vp, _i64, _i64, _d, _d, _vp, C.c_int32]),
     "cov_fire_step": (_i, [_vp, _d, _d, _d, C.c_uint64, _i64, C.c_int32, _pi64]),

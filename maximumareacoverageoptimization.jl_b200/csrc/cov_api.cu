@@ -156,6 +156,7 @@ struct cov_handle {
 
     // scratch
     DevBuf counter, stats, xyT, small_in, argmin_obj, argmin_idx, removed, overflow;
+    DevBuf backup; // mult + cls before an append, restored when the append fails (overflow, mixed weights)
     // forest-fire automaton state (ping-pong) and its direction probabilities
     DevBuf fire[2], fire_p;
     int fire_cur = 0;
@@ -412,7 +413,8 @@ extern "C" void cov_destroy(cov_handle *h)
     cudaStreamSynchronize(h->s_out);
     DevBuf *bufs[] = {&h->mult, &h->cls, &h->planes, &h->params, &h->counter, &h->stats, &h->xyT,
                       &h->small_in, &h->argmin_obj, &h->argmin_idx, &h->removed, &h->overflow, &h->dX,
-                      &h->d_obj, &h->d_count, &h->d_feas, &h->d_clscnt, &h->d_prog, &h->fire[0], &h->fire[1], &h->fire_p};
+                      &h->d_obj, &h->d_count, &h->d_feas, &h->d_clscnt, &h->d_prog, &h->fire[0], &h->fire[1], &h->fire_p,
+                      &h->backup};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (int k = 0; k < 2; ++k)
@@ -470,6 +472,10 @@ extern "C" int cov_set_option(cov_handle *h, int option, int64_t value)
         if (value < -1 || value > 2) return fail(h, COV_ERR_INVALID, "plane mode must be -1..2");
         h->cfg.plane_mode = (int)value;
         return COV_OK;
+    case COV_OPT_PROGRESSIVE_INDEX:
+        if (value < 0 || value > kMaxUavs) return fail(h, COV_ERR_INVALID, "progressive index must be 0..1024");
+        h->o.prog_which = (int)value;
+        return COV_OK;
     }
     return fail(h, COV_ERR_INVALID, "unknown option");
 }
@@ -487,6 +493,7 @@ extern "C" int cov_get_option(const cov_handle *h, int option, int64_t *value)
     case COV_OPT_TRACE: *value = h->trace; return COV_OK;
     case COV_OPT_ZEROCOPY_OUT: *value = h->zero_copy_out; return COV_OK;
     case COV_OPT_PLANE_MODE: *value = h->cfg.plane_mode; return COV_OK;
+    case COV_OPT_PROGRESSIVE_INDEX: *value = h->o.prog_which; return COV_OK;
     }
     return COV_ERR_INVALID;
 }
@@ -645,6 +652,29 @@ static int alloc_cells(cov_handle *h)
     return COV_OK;
 }
 
+// An append (cov_add_points, cov_fire_step) can fail half-way: a multiplicity overflowing 255 or entries of
+// different weights on one cell are found by the kernel that is already writing.  The store is snapshot
+// before and put back on failure, so that mult/cls, the bit planes and n_entries never disagree.
+static int snapshot_cells(cov_handle *h)
+{
+    const size_t ncell = (size_t)h->g.nx * h->g.ny + 4;
+    OK(ensure(h, h->backup, 2 * ncell));
+    CK(cudaMemcpyAsync(h->backup.p, h->mult.p, ncell, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync((char *)h->backup.p + ncell, h->cls.p, ncell, cudaMemcpyDeviceToDevice, h->stream));
+    return COV_OK;
+}
+static void restore_cells(cov_handle *h)
+{
+    const size_t ncell = (size_t)h->g.nx * h->g.ny + 4;
+    cudaError_t e = cudaMemcpyAsync(h->mult.p, h->backup.p, ncell, cudaMemcpyDeviceToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h->cls.p, (char *)h->backup.p + ncell, ncell, cudaMemcpyDeviceToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) { // cannot vouch for the store any more: make the next evaluation fail loudly
+        (void)cudaGetLastError();
+        h->have_grid = false;
+    }
+}
+
 extern "C" int cov_set_grid_bits(cov_handle *h, int64_t nx, int64_t ny, double dx, double dy,
                                  const uint32_t *bits, double weight)
 {
@@ -653,6 +683,7 @@ extern "C" int cov_set_grid_bits(cov_handle *h, int64_t nx, int64_t ny, double d
     if (!bits) return fail(h, COV_ERR_INVALID, "cov_set_grid_bits: bits is NULL");
     OK(check_lattice(h, nx, ny, dx, dy));
     h->have_grid = false;
+    h->have_fire = false; // the automaton's state belongs to the lattice it was initialised on
     describe_lattice(h, nx, ny, dx, dy);
     OK(alloc_cells(h));
     const size_t words = (size_t)ny * ((nx + 31) / 32);
@@ -684,6 +715,7 @@ extern "C" int cov_set_grid_cells(cov_handle *h, int64_t nx, int64_t ny, double 
         for (size_t t = 0; t < ncell; ++t)
             if (cls[t] >= n_classes) return fail(h, COV_ERR_INVALID, "cov_set_grid_cells: class index out of range");
     h->have_grid = false;
+    h->have_fire = false; // the automaton's state belongs to the lattice it was initialised on
     describe_lattice(h, nx, ny, dx, dy);
     OK(alloc_cells(h));
     CK(cudaMemcpyAsync(h->mult.p, mult, ncell, cudaMemcpyHostToDevice, h->stream));
@@ -701,6 +733,7 @@ extern "C" int cov_set_grid_full(cov_handle *h, int64_t nx, int64_t ny, double d
     DeviceGuard dg(h->device);
     OK(check_lattice(h, nx, ny, dx, dy));
     h->have_grid = false;
+    h->have_fire = false; // the automaton's state belongs to the lattice it was initialised on
     describe_lattice(h, nx, ny, dx, dy);
     OK(alloc_cells(h));
     CK(launch_fill_full((unsigned char *)h->mult.p, (unsigned char *)h->cls.p, (long long)nx * ny, h->stream));
@@ -788,6 +821,7 @@ extern "C" int cov_set_points(cov_handle *h, const double *pts5, int64_t P, int6
     if (P < 0 || (P > 0 && !pts5)) return fail(h, COV_ERR_INVALID, "cov_set_points: bad list");
     OK(check_lattice(h, nx, ny, dx, dy));
     h->have_grid = false;
+    h->have_fire = false; // the automaton's state belongs to the lattice it was initialised on
     describe_lattice(h, nx, ny, dx, dy);
     std::vector<int> cell;
     std::vector<unsigned char> pcls;
@@ -823,7 +857,14 @@ extern "C" int cov_add_points(cov_handle *h, const double *pts5, int64_t P)
         n_classes = 1;
         cw[0] = h->g.class_weight[0];
     }
-    OK(upload_points(h, cell, pcls));
+    OK(snapshot_cells(h));
+    const int rc = upload_points(h, cell, pcls);
+    if (rc != COV_OK) { // nothing was appended: the store, its planes and its counts stay as they were
+        const std::string msg = h->err;
+        restore_cells(h);
+        h->err = msg;
+        return rc;
+    }
     return rebuild_planes(h, n_classes, cw);
 }
 
@@ -841,6 +882,14 @@ extern "C" int cov_get_grid_info(const cov_handle *h, cov_grid_info *info)
     info->n_classes = h->g.n_classes;
     info->area_exact = h->area_exact;
     info->planes_in_smem = span_small_applies(h->g, h->have_params ? h->o.N : 1, h->cfg, 0, nullptr, nullptr) ? 1 : 0;
+    return COV_OK;
+}
+
+extern "C" int cov_get_class_weights(const cov_handle *h, double *class_weight, int64_t cap)
+{
+    if (!h || !class_weight) return COV_ERR_INVALID;
+    if (!h->have_grid) return COV_ERR_STATE;
+    for (int64_t k = 0; k < cap && k < h->g.n_classes; ++k) class_weight[k] = h->g.class_weight[k];
     return COV_OK;
 }
 
@@ -959,6 +1008,7 @@ extern "C" int cov_fire_step(cov_handle *h, double wind_speed, double wind_direc
     CK(cudaMemcpyAsync(h->fire_p.p, hp, 9 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemsetAsync(h->removed.p, 0, sizeof(unsigned long long), h->stream));
     CK(cudaMemsetAsync(h->overflow.p, 0, sizeof(int), h->stream));
+    if (append) OK(snapshot_cells(h));
     const int cur = h->fire_cur;
     CK(launch_fire_step((const unsigned char *)h->fire[cur].p, (unsigned char *)h->fire[cur ^ 1].p,
                         (unsigned char *)h->mult.p, (unsigned char *)h->cls.p, h->g.nx, h->g.ny, seed,
@@ -970,9 +1020,13 @@ extern "C" int cov_fire_step(cov_handle *h, double wind_speed, double wind_direc
     CK(cudaMemcpyAsync(hr, h->removed.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(hov, h->overflow.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (*hov) { // the step did not happen: automaton state and cell store stay as they were
+        if (append) restore_cells(h);
+        if (n_pushed) *n_pushed = 0;
+        return fail(h, COV_ERR_LIMIT, "more than 255 list entries on one cell");
+    }
     h->fire_cur = cur ^ 1;
     if (n_pushed) *n_pushed = (int64_t)*hr;
-    if (*hov) return fail(h, COV_ERR_LIMIT, "more than 255 list entries on one cell");
     if (!append || *hr == 0) return COV_OK;
     double cw[kMaxClasses];
     for (int k = 0; k < kMaxClasses; ++k) cw[k] = h->g.class_weight[k];
@@ -1201,6 +1255,9 @@ static int eval_host(cov_handle *h, const double *X, int64_t B, double *obj, int
 {
     OK(check_ready(h, "cov_eval_batch"));
     if (B < 0 || (B > 0 && (!X || !obj))) return fail(h, COV_ERR_INVALID, "cov_eval_batch: bad arguments");
+    if (progressive && h->o.prog_which > h->o.N)
+        return fail(h, COV_ERR_INVALID, "cov_eval_batch_ex: COV_OPT_PROGRESSIVE_INDEX names UAV " +
+                                            std::to_string(h->o.prog_which) + " but N = " + std::to_string(h->o.N));
     if (B == 0) return COV_OK;
     recycle_spans(h);
     const int N = h->o.N;

@@ -19,6 +19,11 @@ __device__ __forceinline__ float int_to_float_small(int i)
 // Julia's max(a, 0.0) for Float64: NaN propagates, max(-0.0, 0.0) = 0.0.
 __device__ __forceinline__ double julia_max0(double v) { return (v != v) ? v : (v > 0.0 ? v : 0.0); }
 
+// The term UAV i (0-based) adds to the progressive output: every UAV for cons1_progressive, one fixed UAV for
+// cons2_progressive / cons3_progressive (src/TDM_Constraints.jl:182-221; `0 + v` is exact, so the single-term
+// forms equal max(R_k - r_max_k, 0.0) itself).
+__device__ __forceinline__ bool prog_takes(const ObjParams &o, int i) { return o.prog_which == 0 || o.prog_which == i + 1; }
+
 __host__ __device__ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 // obj = -area + violation*scale, area from exact integer counts (see cov_grid_info.area_exact)

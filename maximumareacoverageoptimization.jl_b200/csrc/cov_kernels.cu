@@ -121,7 +121,7 @@ __device__ __forceinline__ CandScalars candidate_prologue(const GridDesc &g, con
         if (want_progressive)
             for (int i = 0; i < N; ++i) {
                 const double diff = __dsub_rn(stage[2 * N + i], o.r_max[i]);
-                prog = __dadd_rn(prog, julia_max0(diff));
+                if (prog_takes(o, i)) prog = __dadd_rn(prog, julia_max0(diff));
             }
     }
     r.violation = __shfl_sync(0xffffffffu, viol, 0);

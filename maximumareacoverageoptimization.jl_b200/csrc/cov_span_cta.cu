@@ -140,7 +140,7 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
             for (int i = 0; i < N; ++i) {
                 const double diff = __dsub_rn(stage[2 * N + i], o.r_max[i]);
                 viol = __dadd_rn(viol, fabs(diff));
-                if (out.progressive) prog = __dadd_rn(prog, julia_max0(diff));
+                if (out.progressive && prog_takes(o, i)) prog = __dadd_rn(prog, julia_max0(diff));
             }
             *s_viol = viol;
             *s_prog = prog;

@@ -153,7 +153,7 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
             for (int i = 0; i < N; ++i) {
                 const double diff = __dsub_rn(rr[i], par[i]);
                 my_viol = __dadd_rn(my_viol, fabs(diff));
-                if (out.progressive) my_prog = __dadd_rn(my_prog, julia_max0(diff));
+                if (out.progressive && prog_takes(o, i)) my_prog = __dadd_rn(my_prog, julia_max0(diff));
             }
             bool bad = false;
             if (o.use_cons3) {

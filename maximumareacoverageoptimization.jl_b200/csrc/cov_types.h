@@ -38,6 +38,8 @@ struct GridDesc {
 struct ObjParams {
     int N;
     int use_cons3, use_cons7, use_cons8;
+    int prog_which;         // progressive output: 0 = sum over every UAV (cons1_progressive), k >= 1 = UAV k only
+                            // (cons2_progressive: k = 2, cons3_progressive: k = 3; src/TDM_Constraints.jl:182-221)
     double penalty_scale;   // 1e5
     double tan_half_fov;
     double cons7_R;         // fl(19 * tan_half_fov)

@@ -61,6 +61,10 @@ class CoverageEngine:
         self.device = int(device)
         self.N = None
         self._pinned = []
+        # Who configured the closure parameters last: every set_params() clears it, and a caller that wants
+        # to skip redundant uploads stores its own token here afterwards and compares before each use
+        # (several objectives / constraints share one engine and must not run on each other's r_max).
+        self.param_owner = None
 
     # ---- plumbing ----
     def _check(self, rc: int):
@@ -144,6 +148,13 @@ class CoverageEngine:
         self._check(lib.cov_get_grid_info(self._h, C.byref(gi)))
         return {f: getattr(gi, f) for f, _ in _lib.GridInfo._fields_}
 
+    def class_weights(self) -> list:
+        """Weight of every class as the device numbers them (the k of `class_count[:, k]`)."""
+        n = self.grid_info()["n_classes"]
+        w = (C.c_double * max(n, 1))()
+        self._check(lib.cov_get_class_weights(self._h, w, n))
+        return [float(w[k]) for k in range(n)]
+
     def grid_cells(self) -> np.ndarray:
         gi = self.grid_info()
         out = np.empty(gi["nx"] * gi["ny"], dtype=np.uint8)
@@ -200,6 +211,7 @@ class CoverageEngine:
                                        _ptr(d_lim) if prev_xyR is not None else None, tan_half_fov,
                                        float(sep_min), 1 if use_cons7 else 0))
         self.N = int(N)
+        self.param_owner = None
 
     # ---- evaluation ----
     def eval_batch(self, X, want_count=True, want_feasible=True, want_class_count=False,

@@ -116,6 +116,12 @@ def cons1_progressive(x, r_max) -> float:
     return lib().orc_cons1_progressive(_p(x), x.size // 3, _p(r_max))
 
 
+def consK_progressive(x, r_max, which: int) -> float:
+    """cons2_progressive (which = 2) / cons3_progressive (which = 3), src/TDM_Constraints.jl:197-221."""
+    x, r_max = _f(x).ravel(), _f(r_max).ravel()
+    return lib().orc_consK_progressive(_p(x), x.size // 3, _p(r_max), which)
+
+
 def rmvCoveredPOI(circles, pts5) -> np.ndarray:
     circles = _f(circles).ravel()
     pts = _f(pts5).reshape(-1, 5).copy()

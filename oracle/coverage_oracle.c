@@ -141,6 +141,10 @@ ORC_API int orc_cons8(const double *x, int64_t N, double sep)
     return 1;
 }
 
+/* Julia's max(v, 0.0) on Float64: NaN propagates (C's fmax would return 0.0 for a NaN), and
+ * max(-0.0, 0.0) is +0.0. */
+static inline double orc_julia_max0(double v) { return (v != v) ? v : (v > 0.0 ? v : 0.0); }
+
 /* src/TDM_Constraints.jl:182-195  cons1_progressive(x) = sum max(R_i - r_max_i, 0.0).
  * (`violation = 0` starts as an Int and is promoted on the first add; 0 + v is exact.) */
 ORC_API double orc_cons1_progressive(const double *x, int64_t N, const double *r_max)
@@ -148,7 +152,7 @@ ORC_API double orc_cons1_progressive(const double *x, int64_t N, const double *r
     double violation = 0;
     for (int64_t i = 0; i < N; ++i) {
         double R_val = x[2 * N + i];
-        violation += fmax(R_val - r_max[i], 0.0);
+        violation += orc_julia_max0(R_val - r_max[i]);
     }
     return violation;
 }
@@ -159,7 +163,7 @@ ORC_API double orc_consK_progressive(const double *x, int64_t N, const double *r
 {
     double violation = 0;
     double R_val = x[2 * N + (which - 1)];
-    violation += fmax(R_val - r_max[which - 1], 0.0);
+    violation += orc_julia_max0(R_val - r_max[which - 1]);
     return violation;
 }
 

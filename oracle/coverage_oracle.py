@@ -127,13 +127,30 @@ def cons8(x, sep: float = 15.0) -> bool:
     return True
 
 
+def _julia_max0(v: float) -> float:
+    """Julia's max(v, 0.0) on Float64: NaN propagates, max(-0.0, 0.0) is +0.0."""
+    if v != v:
+        return v
+    return v if v > 0.0 else 0.0
+
+
 def cons1_progressive(x, r_max) -> float:
     """src/TDM_Constraints.jl:182-195."""
     x = np.asarray(x, dtype=np.float64)
     n = len(x) // 3
     violation = 0.0
     for i in range(n):
-        violation += max(float(x[2 * n + i]) - float(r_max[i]), 0.0)
+        violation += _julia_max0(float(x[2 * n + i]) - float(r_max[i]))
+    return violation
+
+
+def consK_progressive(x, r_max, which: int) -> float:
+    """src/TDM_Constraints.jl:197-221 -- cons2_progressive (which = 2) / cons3_progressive (which = 3):
+    the same term for ONE fixed UAV, 1-based index as in the reference."""
+    x = np.asarray(x, dtype=np.float64)
+    n = len(x) // 3
+    violation = 0
+    violation += _julia_max0(float(x[2 * n + which - 1]) - float(r_max[which - 1]))
     return violation
 
 

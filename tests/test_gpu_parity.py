@@ -16,6 +16,13 @@ def rand_candidates(rng, B, N, extent=500.0, hmin=5.0, hmax=30.0):
     return np.concatenate([rng.random((B, 2 * N)) * extent, (hmin + rng.random((B, N)) * (hmax - hmin)) * T], axis=1)
 
 
+def same_doubles(a, b):
+    """Bit-identical, except that any NaN equals any NaN (payloads are not part of the contract)."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    na, nb = np.isnan(a), np.isnan(b)
+    return np.array_equal(na, nb) and np.array_equal(a[~na].view(np.uint64), b[~nb].view(np.uint64))
+
+
 def check_against_oracle(cov, orc, eng, X, N, r_max, pts, **cons):
     want = orc.eval_batch(X, N, r_max, pts, want_prog=True, **cons)
     got = eng.eval_batch(X, want_progressive=True)
@@ -228,13 +235,21 @@ def test_edge_radii_and_far_centres(cov, orc, engine):
     ], dtype=np.float64)
     for kernel in ("span", "span_general", "brute", "exact"):
         engine.set_option(cov.OPT_KERNEL, KERNELS[kernel])
-        want = orc.eval_batch(X, N, r_max, pts)
-        got = engine.eval_batch(X)
-        assert np.array_equal(got["count"], want["count"]), (kernel, got["count"], want["count"])
-        assert np.array_equal(got["obj"].view(np.uint64) | (np.isnan(got["obj"]) * np.uint64(0)),
-                              want["obj"].view(np.uint64)) or (
-            np.array_equal(np.isnan(got["obj"]), np.isnan(want["obj"])) and
-            np.array_equal(got["obj"][~np.isnan(got["obj"])], want["obj"][~np.isnan(want["obj"])]))
+        want = orc.eval_batch(X, N, r_max, pts, want_prog=True)
+        for which in (0, 1, 2):  # cons1_progressive, then the single-UAV forms (src/TDM_Constraints.jl:182-221)
+            engine.set_option(cov.OPT_PROGRESSIVE_INDEX, which)
+            got = engine.eval_batch(X, want_progressive=True)
+            assert np.array_equal(got["count"], want["count"]), (kernel, got["count"], want["count"])
+            assert same_doubles(got["obj"], want["obj"]), (kernel, got["obj"], want["obj"])
+            wp = want["progressive"] if which == 0 else np.array([orc.consK_progressive(x, r_max, which) for x in X])
+            # NaN R (row 2), inf - inf (row 10): Julia's max(NaN, 0.0) is NaN and the sums carry it
+            assert same_doubles(got["progressive"], wp), (kernel, which, got["progressive"], wp)
+            assert np.isnan(wp[2]) == (which in (0, 1)) and np.isnan(wp[10]) == (which in (0, 1))
+        engine.set_option(cov.OPT_PROGRESSIVE_INDEX, 0)
+    engine.set_option(cov.OPT_PROGRESSIVE_INDEX, 3)  # UAV 3 of a 2-UAV swarm
+    with pytest.raises(cov.CoverageError):
+        engine.eval_batch(X, want_progressive=True)
+    engine.set_option(cov.OPT_PROGRESSIVE_INDEX, 0)
 
 
 def test_empty_inputs(cov, orc, engine):
@@ -405,6 +420,15 @@ def test_reference_api_static(cov, orc, kat):
     assert cons7.batch(Xc).tolist() == [orc.cons7(x, T) for x in Xc]
     prog = TC.create_cons1_progressive(5, r_max)
     assert prog.batch(Xc).tolist() == [orc.cons1_progressive(x, r_max) for x in Xc]
+    Xp = Xc.copy()
+    Xp[:, 10:] += rng.normal(0, 30, (300, 5))  # radii on both sides of r_max
+    prog2, prog3 = TC.create_cons2_progressive(5, r_max), TC.create_cons3_progressive(5, r_max)
+    assert prog2.batch(Xp).tolist() == [orc.consK_progressive(x, r_max, 2) for x in Xp]  # src/TDM_Constraints.jl:197-208
+    assert prog3.batch(Xp).tolist() == [orc.consK_progressive(x, r_max, 3) for x in Xp]  # :210-221
+    assert prog.batch(Xp).tolist() == [orc.cons1_progressive(x, r_max) for x in Xp]      # and back to the sum
+    assert prog2(Xp[0]) == orc.consK_progressive(Xp[0], r_max, 2) and (prog2.batch(Xp) > 0).any()
+    with pytest.raises(ValueError):
+        TC.create_cons3_progressive(2, r_max[:2])
     # fused constraints
     rest = obj.fuse([TC.cons1, cons3, lambda x: True])
     assert len(rest) == 1
@@ -965,3 +989,154 @@ def test_auto_routing_by_batch_size(cov, orc, engine):
         assert np.array_equal(got["count"], want["count"][:B]) and np.array_equal(got["feasible"], want["feasible"][:B])
         assert np.array_equal(got["obj"].view(np.uint64), want["obj"][:B].view(np.uint64))
     assert engine.eval_one(X[5]) == want["obj"][5]
+
+
+# ---------------------------------------------------------------- round-2 regressions and larger direct samples
+def test_class_numbering_survives_removals(cov, orc, engine, fire_rows):
+    """Two dyadic weight classes (25 and 250): after rmvCoveredPOI deletes the leading entries of the first
+    class -- and then every entry of it -- the host list's order of first appearance no longer matches the
+    device's class numbering; calculateArea must still pair counts with the right weights."""
+    ACC = cov.AreaCoverageCalculation
+    allp = np.concatenate(fire_rows[:30]).copy()
+    assert allp[0, 3] == 25.0
+    first_xy = allp[0, :2].copy()
+    heavy = (allp[:, 0] > first_xy[0] + 40)
+    allp[heavy, 3] = 250.0
+    assert 0 < heavy.sum() < len(allp)
+    pl = ACC.PointList(allp, 100, 100, 5.0, 5.0)
+    res = ACC.ResidentList(pl, engine=engine)
+    eng = res.sync()
+    assert eng.grid_info()["area_exact"] == 1 and eng.class_weights() == [25.0, 250.0]
+    rng = np.random.default_rng(5)
+    probe = rand_candidates(rng, 40, 4)
+    probe[:, 4:8] = 200 + probe[:, 4:8] * 0.3
+
+    def check():
+        for x in probe:
+            area, cnt, _ = orc.calculateArea(x, res.points.data)
+            assert ACC.calculateArea(x, res) == area
+    check()
+    # delete the leading entries of the light class: the host list now starts with ... whatever is left
+    ACC.rmvCoveredPOI(np.array([first_xy[0], first_xy[1], 12.0]), res)
+    assert np.array_equal(res.points.data, orc.rmvCoveredPOI(np.array([first_xy[0], first_xy[1], 12.0]), allp))
+    check()
+    # delete EVERY light entry (x <= first_x + 40): the host list has one distinct weight, the device still two classes
+    light = res.points.data[res.points.data[:, 3] == 25.0]
+    big = np.array([light[:, 0].min() - 200.0, light[:, 1].mean(), 0.0])
+    big[2] = np.abs(light[:, 0] - big[0]).max() + 1.0
+    while (res.points.data[:, 3] == 25.0).any():
+        xy = res.points.data[res.points.data[:, 3] == 25.0][0, :2]
+        ACC.rmvCoveredPOI(np.array([xy[0] - 30.0, xy[1], 32.0]), res)
+    assert len(res.points) > 0 and (res.points.data[:, 3] == 250.0).all()
+    check()
+
+
+def test_store_state_after_relattice_and_failed_appends(cov, orc, engine):
+    """ADVICE: (1) a grid setter after cov_fire_init must invalidate the automaton (its buffers belong to the old
+    lattice); (2) a failing append leaves store, planes and counts exactly as they were."""
+    rng = np.random.default_rng(12)
+    state = (rng.random(40 * 40) < 0.7).astype(np.uint8)
+    state[:80] = 2
+    engine.fire_init(state, 40, 40, 5.0, 5.0)
+    engine.fire_step(4.0, 270 / 180 * math.pi, 0.5, seed=3, step=1)
+    engine.set_grid_full(300, 300, 1.0, 1.0)  # a LARGER lattice
+    with pytest.raises(cov.CoverageError) as ei:
+        engine.fire_step(4.0, 270 / 180 * math.pi, 0.5, seed=3, step=2)
+    assert ei.value.code == cov._lib.COV_ERR_STATE
+    with pytest.raises(cov.CoverageError):
+        engine.fire_state()
+    # mixed weights on one cell / multiplicity overflow: rejected, and nothing changed
+    pts = orc.createPOI(5.0, 5.0, 20.0, 20.0)
+    engine.set_points(pts, 20, 20, 5.0, 5.0)
+    N = 2
+    r_max = np.full(N, 30 * T)
+    engine.set_params(N, r_max)
+    X = rand_candidates(rng, 300, N, extent=100.0)
+    before = engine.eval_batch(X)
+    info0, cells0 = engine.grid_info(), engine.grid_cells()
+    bad = pts[:50].copy()
+    bad[25:, 3] = 99.0
+    with pytest.raises(cov.CoverageError):
+        engine.add_points(bad)
+    many = np.repeat(pts[7:8], 300, axis=0)  # 1 + 300 entries on one cell
+    with pytest.raises(cov.CoverageError) as ei:
+        engine.add_points(np.concatenate([pts[100:140], many]))
+    assert ei.value.code == cov._lib.COV_ERR_LIMIT
+    assert engine.grid_info() == info0 and np.array_equal(engine.grid_cells(), cells0)
+    after = engine.eval_batch(X)
+    assert np.array_equal(before["count"], after["count"]) and np.array_equal(before["obj"], after["obj"])
+    engine.add_points(pts[:50])  # and a good append still works
+    now = np.concatenate([pts, pts[:50]])
+    check_against_oracle(cov, orc, engine, X, N, r_max, now)
+
+
+def test_two_objectives_share_one_engine(cov, orc):
+    """ADVICE: two closures on the same Cells with different r_max / fused constraints, called alternately."""
+    CF, OPT, TC = cov.CellFunctions, cov.TDM_STATIC_opt, cov.TDM_Constraints
+    cells = CF.initialise_POI(CF.Cells(), "static")
+    pts = cells.points_of_interest.data
+    N = 5
+    r1, r2 = np.full(N, 30 * T), np.full(N, 12 * T)
+    f1, f2 = OPT.createObjective(cells, N, r1), OPT.createObjective(cells, N, r2)
+    rng = np.random.default_rng(2)
+    X = rand_candidates(rng, 64, N)
+    pre = X[0]
+    f2.fuse([TC.create_cons3(pre, 100 / 180 * math.pi, 10.0)])
+    for k in range(6):
+        x = X[k]
+        assert f1(x) == orc.objective(x, r1, pts)[0]
+        assert f2(x) == orc.objective(x, r2, pts)[0]
+        two = np.array([x[0], x[1], x[N], x[N + 1], x[2 * N], x[2 * N + 1]])  # calculateArea with another N in between
+        assert cov.AreaCoverageCalculation.calculateArea(two, cells.resident()) == orc.calculateArea(two, pts)[0]
+    o1 = f1.batch(X)
+    o2, fe2 = f2.batch(X, want_feasible=True)
+    o1b, fe1 = f1.batch(X, want_feasible=True)
+    assert np.array_equal(o1, orc.eval_batch(X, N, r1, pts)["obj"]) and np.array_equal(o1, o1b) and fe1.all()
+    want2 = orc.eval_batch(X, N, r2, pts, pre=pre, d_lim=10.0, tan_half_fov=T)
+    assert np.array_equal(o2, want2["obj"]) and np.array_equal(fe2, want2["feasible"].astype(bool))
+    cells.close()
+
+
+def _philox_batch(cov, engine, B, N, seed, first=0):
+    dX = engine.device_alloc(B * 3 * N * 8)
+    engine.generate_candidates(dX, B, N, seed=seed, first_index=first)
+    X = np.empty((B, 3 * N))
+    engine.memcpy_d2h(X, dX)
+    engine.sync()
+    engine.device_free(dX)
+    return X
+
+
+@pytest.mark.slow
+def test_c3_direct_oracle_sample_10k(cov, orc, engine):
+    """C3 (50 UAVs, 1024^2, cons8) against the literal CPU restatement on >= 10^4
+    candidates -- half NumPy-seeded, half generated on the device by Philox (what the full-size runs use)."""
+    n, N = 1024, 50
+    d = 500.0 / n
+    bits, nset = cov.synth.fire_grid(n)
+    pts = cov.synth.points_from_bits(bits, n, d, d)
+    engine.set_grid_bits(bits, n, n, d, d)
+    r_max = np.full(N, 30 * T)
+    engine.set_params(N, r_max, sep_min=15.0)
+    Xd = _philox_batch(cov, engine, 6000, N, seed=404, first=3_999_000)
+    assert np.array_equal(Xd, cov.synth.philox_candidates(6000, N, 404, 3_999_000))
+    X = np.concatenate([cov.synth.random_candidates(6000, N, seed=12), Xd])
+    got = check_against_oracle(cov, orc, engine, X, N, r_max, pts, sep_min=15.0)
+    assert len(X) >= 10_000 and got["count"].min() > 0
+
+
+@pytest.mark.slow
+def test_c4_direct_oracle_sample_1k(cov, orc, engine):
+    """C4 (200 UAVs, 4096^2, cons8): >= 10^3 candidates against the literal CPU restatement (~10^12 predicate
+    evaluations on the host cores), half of them Philox candidates from the far end of the 16 M index range."""
+    n, N = 4096, 200
+    d = 500.0 / n
+    bits, nset = cov.synth.fire_grid(n)
+    pts = cov.synth.points_from_bits(bits, n, d, d)
+    engine.set_grid_bits(bits, n, n, d, d)
+    r_max = np.full(N, 30 * T)
+    engine.set_params(N, r_max, sep_min=15.0)
+    Xd = _philox_batch(cov, engine, 512, N, seed=8, first=16_000_000 - 512)
+    X = np.concatenate([cov.synth.random_candidates(512, N, seed=13), Xd])
+    check_against_oracle(cov, orc, engine, X, N, r_max, pts, sep_min=15.0)
+    assert len(X) >= 1000

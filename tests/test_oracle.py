@@ -67,6 +67,35 @@ def test_c_vs_numpy_random(orc, npo):
         assert np.array_equal(orc.rmvCoveredPOI(x, pts), npo.rmvCoveredPOI(x, pts))
 
 
+def test_progressive_julia_max_semantics(orc, npo):
+    """src/TDM_Constraints.jl:182-221: Julia's max(v, 0.0) propagates NaN (C's fmax would not) and
+    max(-0.0, 0.0) is +0.0; both restatements must agree bit for bit, for cons1/2/3_progressive."""
+    nan, inf = math.nan, math.inf
+    r_max = np.array([10.0, 20.0, 30.0, inf])
+    rows = [
+        [0, 0, 0, 0, 0, 0, 0, 0, 12.0, 19.0, nan, 1.0],    # NaN radius: every sum it enters is NaN
+        [0, 0, 0, 0, 0, 0, 0, 0, nan, 25.0, 31.0, 1.0],
+        [0, 0, 0, 0, 0, 0, 0, 0, inf, 20.0, 30.0, inf],    # inf - inf = NaN for UAV 4
+        [0, 0, 0, 0, 0, 0, 0, 0, 10.0, 20.0, 30.0, -inf],  # all differences <= 0 (one is -0.0 + ...)
+        [0, 0, 0, 0, 0, 0, 0, 0, 10.0, 20.5, 29.0, 5.0],
+        [0, 0, 0, 0, 0, 0, 0, 0, -0.0, 1e308, 1e-320, 0.0],
+    ]
+    for x in rows:
+        x = np.array(x)
+        a, b = orc.cons1_progressive(x, r_max), npo.cons1_progressive(x, r_max)
+        assert np.float64(a).view(np.uint64) == np.float64(b).view(np.uint64) or (a != a and b != b), (x, a, b)
+        for which in (1, 2, 3, 4):
+            a, b = orc.consK_progressive(x, r_max, which), npo.consK_progressive(x, r_max, which)
+            assert np.float64(a).view(np.uint64) == np.float64(b).view(np.uint64) or (a != a and b != b), (x, which)
+    assert math.isnan(orc.cons1_progressive(np.array(rows[0]), r_max))
+    assert math.isnan(orc.consK_progressive(np.array(rows[0]), r_max, 3))
+    assert orc.consK_progressive(np.array(rows[0]), r_max, 2) == 0.0
+    assert orc.consK_progressive(np.array(rows[4]), r_max, 2) == 0.5
+    assert math.copysign(1.0, orc.consK_progressive(np.array(rows[3]), r_max, 1)) == 1.0  # +0.0, not -0.0
+    out = orc.eval_batch(np.array(rows), 4, r_max, orc.createPOI(5.0, 5.0, 4.0, 4.0), want_prog=True)
+    assert np.isnan(out["progressive"][:3]).all() and out["progressive"][4] == 0.5
+
+
 def test_batch_matches_scalar_and_threads(orc):
     rng = np.random.default_rng(11)
     pts = orc.createPOI(5.0, 5.0, 40.0, 40.0)
