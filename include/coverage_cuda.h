@@ -206,6 +206,12 @@ COV_API int cov_eval_one(cov_handle *h, const double *x, double *obj);
 COV_API int cov_argmin(cov_handle *h, const double *X, int64_t B, int32_t barrier, double *best_obj,
                int64_t *best_idx);
 
+/* cov_eval_batch and the poll winner in one call: the per-candidate outputs as above (obj nullable here) plus
+ * (best_obj, best_idx) reduced on the device -- the 16 bytes a rank contributes to the (min, index) exchange
+ * when the candidates of one poll are sharded over several GPUs. */
+COV_API int cov_eval_batch_best(cov_handle *h, const double *X, int64_t B, double *obj, int64_t *count,
+                        uint8_t *feasible, int32_t barrier, double *best_obj, int64_t *best_idx);
+
 /* A whole MADS solve in native code: the batch producer the reference lacks (DirectSearch.jl evaluates one
  * trial point per call). Settings of TDM_STATIC_opt.optimize (src/TDM_STATIC_opt.jl:118-222): start point x0
  * (3N), iteration limit n_iter (100 there), the same granularity on every variable (1.0 there), the enabled
@@ -253,6 +259,11 @@ typedef struct cov_launch_info {
     int32_t smem_bytes;     /* dynamic shared memory per CTA */
     int32_t band_rows;      /* framebuffer rows per band (ny: a single band) */
     int32_t planes_in_smem; /* 1: bit planes staged in shared memory */
+    /* the template instantiation that ran (ABI 2; names the ncu profile bench.py's issue roofline reads) */
+    int32_t multi;          /* 1: several bit planes / weight classes / multiplicities */
+    int32_t chunk;          /* small-swarm kernel: candidates per work unit; else 0 */
+    int32_t max_warps;      /* small-swarm kernel: warps per CTA the instantiation allows (20 or 24); else 0 */
+    int32_t plane_mode;     /* CTA kernel: COV_OPT_PLANE_MODE it resolved to (0, 1, 2); else -1 */
 } cov_launch_info;
 COV_API int cov_last_launch(const cov_handle *h, cov_launch_info *out);
 /* Running totals over every coverage-kernel launch of this handle: summed device time (CUDA

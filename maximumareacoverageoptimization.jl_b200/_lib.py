@@ -33,7 +33,8 @@ class GridInfo(C.Structure):
 
 class LaunchInfo(C.Structure):
     _fields_ = [("kernel", C.c_int32), ("grid", C.c_int32), ("block", C.c_int32), ("smem_bytes", C.c_int32),
-                ("band_rows", C.c_int32), ("planes_in_smem", C.c_int32)]
+                ("band_rows", C.c_int32), ("planes_in_smem", C.c_int32), ("multi", C.c_int32), ("chunk", C.c_int32),
+                ("max_warps", C.c_int32), ("plane_mode", C.c_int32)]
 
 
 class Limits(C.Structure):
@@ -70,6 +71,7 @@ SIGNATURES = {
     "cov_eval_batch_ex": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "cov_eval_batch_device": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "cov_eval_one": (_i, [_vp, _vp, _pd]),
+    "cov_eval_batch_best": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, C.c_int32, _pd, _pi64]),
     "cov_argmin": (_i, [_vp, _vp, _i64, C.c_int32, _pd, _pi64]),
     "cov_union_area_batch": (_i, [_vp, _vp, _i64, _i64, _vp]),
     "cov_mads_solve": (_i, [_vp, _vp, _i64, _d, C.c_uint64, _vp, _pd, _pi64]),

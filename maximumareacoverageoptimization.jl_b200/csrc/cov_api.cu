@@ -1250,11 +1250,19 @@ static int eval_host_small(cov_handle *h, const double *X, int64_t B, double *ob
     return COV_OK;
 }
 
+// The poll winner of a host-path call (cov_argmin, cov_eval_batch_best): reduced on the device from the
+// device-resident copy of the objectives and flags, 16 bytes come back per window.
+struct BestReq {
+    int barrier;
+    double best = INFINITY;
+    int64_t idx = -1;
+};
+
 static int eval_host(cov_handle *h, const double *X, int64_t B, double *obj, int64_t *count, uint8_t *feasible,
-                     int64_t *class_count, double *progressive)
+                     int64_t *class_count, double *progressive, BestReq *best = nullptr)
 {
     OK(check_ready(h, "cov_eval_batch"));
-    if (B < 0 || (B > 0 && (!X || !obj))) return fail(h, COV_ERR_INVALID, "cov_eval_batch: bad arguments");
+    if (B < 0 || (B > 0 && (!X || (!obj && !best)))) return fail(h, COV_ERR_INVALID, "cov_eval_batch: bad arguments");
     if (progressive && h->o.prog_which > h->o.N)
         return fail(h, COV_ERR_INVALID, "cov_eval_batch_ex: COV_OPT_PROGRESSIVE_INDEX names UAV " +
                                             std::to_string(h->o.prog_which) + " but N = " + std::to_string(h->o.N));
@@ -1263,12 +1271,12 @@ static int eval_host(cov_handle *h, const double *X, int64_t B, double *obj, int
     const int N = h->o.N;
     const int ncls = h->g.n_classes;
     const size_t row_bytes = (size_t)3 * N * 8;
-    if ((size_t)B * row_bytes <= (256u << 10) && (size_t)B * (25 + 8 * (size_t)ncls) <= (1536u << 10) && h->chunk == 0)
+    if (!best && (size_t)B * row_bytes <= (256u << 10) && (size_t)B * (25 + 8 * (size_t)ncls) <= (1536u << 10) && h->chunk == 0)
         return eval_host_small(h, X, B, obj, count, feasible, class_count, progressive);
 #if COV_ZC_MID_LIMIT > 0
     // mid-size batches in pinned buffers: one launch that reads the candidates straight over PCIe (the
     // kernel's own unit prefetch overlaps transfer and compute) and writes the results back the same way
-    if (h->zero_copy_out && h->chunk == 0 && N <= 8 && (size_t)B * row_bytes <= (size_t)(COV_ZC_MID_LIMIT) && is_pinned_host(X) &&
+    if (!best && h->zero_copy_out && h->chunk == 0 && N <= 8 && (size_t)B * row_bytes <= (size_t)(COV_ZC_MID_LIMIT) && is_pinned_host(X) &&
         is_pinned_host(obj) && (!count || is_pinned_host(count)) && (!feasible || is_pinned_host(feasible)) &&
         (!class_count || is_pinned_host(class_count)) && (!progressive || is_pinned_host(progressive))) {
         const double *vx = (const double *)device_view((void *)X);
@@ -1294,7 +1302,7 @@ static int eval_host(cov_handle *h, const double *X, int64_t B, double *obj, int
     OK(ensure(h, h->dX, (size_t)window * row_bytes));
     OK(ensure(h, h->d_obj, (size_t)window * 8));
     if (count) OK(ensure(h, h->d_count, (size_t)window * 8));
-    if (feasible) OK(ensure(h, h->d_feas, (size_t)window));
+    if (feasible || best) OK(ensure(h, h->d_feas, (size_t)window));
     if (class_count) OK(ensure(h, h->d_clscnt, (size_t)window * 8 * ncls));
     if (progressive) OK(ensure(h, h->d_prog, (size_t)window * 8));
     const bool in_pinned = is_pinned_host(X);
@@ -1305,7 +1313,7 @@ static int eval_host(cov_handle *h, const double *X, int64_t B, double *obj, int
             if (k == 1) h->h_in_cap = cap;
         }
     // outputs that are not pinned are staged per window and copied out at the window's end
-    const bool obj_p = is_pinned_host(obj), cnt_p = !count || is_pinned_host(count),
+    const bool obj_p = !obj || is_pinned_host(obj), cnt_p = !count || is_pinned_host(count),
                fea_p = !feasible || is_pinned_host(feasible), cls_p = !class_count || is_pinned_host(class_count),
                prg_p = !progressive || is_pinned_host(progressive);
     size_t stage_out = 0;
@@ -1372,7 +1380,7 @@ static int eval_host(cov_handle *h, const double *X, int64_t B, double *obj, int
             tr(h->stream);
             EvalOut out{};
             const int64_t g0 = w0 + c0;
-            bool zc = h->zero_copy_out != 0;
+            bool zc = h->zero_copy_out != 0 && !best; // the winner is reduced from device-resident results
             if (zc) {
                 // results go straight to pinned host memory (the caller's buffer, or the staging block): posted
                 // PCIe writes of 17 B per candidate instead of three D2H copies per slice beside the H2D stream
@@ -1394,7 +1402,7 @@ static int eval_host(cov_handle *h, const double *X, int64_t B, double *obj, int
             if (!zc) {
                 out.obj = (double *)h->d_obj.p + c0;
                 out.count = count ? (long long *)h->d_count.p + c0 : nullptr;
-                out.feasible = feasible ? (unsigned char *)h->d_feas.p + c0 : nullptr;
+                out.feasible = (feasible || best) ? (unsigned char *)h->d_feas.p + c0 : nullptr;
                 out.class_count = class_count ? (long long *)h->d_clscnt.p + (size_t)c0 * ncls : nullptr;
                 out.progressive = progressive ? (double *)h->d_prog.p + c0 : nullptr;
             }
@@ -1404,8 +1412,9 @@ static int eval_host(cov_handle *h, const double *X, int64_t B, double *obj, int
             tr(h->stream);
             if (!zc) {
                 CKD(cudaStreamWaitEvent(h->s_out, ev_k, 0));
-                CKD(cudaMemcpyAsync(obj_p ? (void *)(obj + g0) : (void *)(so + off_obj + (size_t)c0 * 8), out.obj,
-                                    (size_t)cn * 8, cudaMemcpyDeviceToHost, h->s_out));
+                if (obj)
+                    CKD(cudaMemcpyAsync(obj_p ? (void *)(obj + g0) : (void *)(so + off_obj + (size_t)c0 * 8), out.obj,
+                                        (size_t)cn * 8, cudaMemcpyDeviceToHost, h->s_out));
                 if (count)
                     CKD(cudaMemcpyAsync(cnt_p ? (void *)(count + g0) : (void *)(so + off_cnt + (size_t)c0 * 8),
                                         out.count, (size_t)cn * 8, cudaMemcpyDeviceToHost, h->s_out));
@@ -1423,6 +1432,20 @@ static int eval_host(cov_handle *h, const double *X, int64_t B, double *obj, int
             tr(zc ? h->stream : h->s_out);
         }
         // end of window: results home, device window reusable
+        if (best) {
+            CKD(launch_argmin((const double *)h->d_obj.p, (const unsigned char *)h->d_feas.p, wn, best->barrier,
+                              (double *)h->argmin_obj.p, (long long *)h->argmin_idx.p, 1024, h->stream));
+            h->launches += 2;
+            double *ho = (double *)h->h_small + 40;
+            long long *hi = (long long *)h->h_small + 41;
+            CKD(cudaMemcpyAsync(ho, h->argmin_obj.p, 8, cudaMemcpyDeviceToHost, h->stream));
+            CKD(cudaMemcpyAsync(hi, h->argmin_idx.p, 8, cudaMemcpyDeviceToHost, h->stream));
+            CKD(cudaStreamSynchronize(h->stream));
+            if (*hi >= 0 && (best->idx < 0 || *ho < best->best)) { // ties keep the earlier window's index
+                best->best = *ho;
+                best->idx = w0 + *hi;
+            }
+        }
         CKD(cudaStreamSynchronize(h->stream));
         CKD(cudaStreamSynchronize(h->s_out));
         if (!obj_p) host_copy(h, obj + w0, so + off_obj, (size_t)wn * 8);
@@ -1456,6 +1479,19 @@ extern "C" int cov_eval_batch_ex(cov_handle *h, const double *X, int64_t B, doub
     if (!h) return fail(nullptr, COV_ERR_INVALID, "NULL handle");
     DeviceGuard dg(h->device);
     return eval_host(h, X, B, obj, count, feasible, class_count, progressive);
+}
+
+extern "C" int cov_eval_batch_best(cov_handle *h, const double *X, int64_t B, double *obj, int64_t *count,
+                                   uint8_t *feasible, int32_t barrier, double *best_obj, int64_t *best_idx)
+{
+    if (!h) return fail(nullptr, COV_ERR_INVALID, "NULL handle");
+    DeviceGuard dg(h->device);
+    if (!best_obj || !best_idx) return fail(h, COV_ERR_INVALID, "cov_eval_batch_best: NULL winner outputs");
+    BestReq br{barrier};
+    OK(eval_host(h, X, B, obj, count, feasible, nullptr, nullptr, &br));
+    *best_obj = br.idx >= 0 ? br.best : INFINITY;
+    *best_idx = br.idx;
+    return COV_OK;
 }
 
 // One candidate through pinned scratch: copy in, one launch, copy out, one synchronisation.
@@ -1683,9 +1719,16 @@ extern "C" int cov_argmin(cov_handle *h, const double *X, int64_t B, int32_t bar
     if (B < 0 || (B > 0 && !X) || !best_obj || !best_idx) return fail(h, COV_ERR_INVALID, "cov_argmin: bad arguments");
     double best = INFINITY;
     int64_t bidx = -1;
-    recycle_spans(h);
     const int N = h->o.N;
     const size_t row_bytes = (size_t)3 * N * 8;
+    if ((size_t)B * row_bytes > (4u << 20)) { // big sets: the sliced pipeline (H2D of slice k+1 beside the kernel of slice k)
+        BestReq br{barrier};
+        OK(eval_host(h, X, B, nullptr, nullptr, nullptr, nullptr, nullptr, &br));
+        *best_obj = br.idx >= 0 ? br.best : INFINITY;
+        *best_idx = br.idx;
+        return COV_OK;
+    }
+    recycle_spans(h);
     const int64_t window = std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(B, 1), (int64_t)((1ull << 30) / row_bytes)));
     OK(ensure(h, h->dX, (size_t)window * row_bytes));
     OK(ensure(h, h->d_obj, (size_t)window * 8));
@@ -1846,6 +1889,10 @@ extern "C" int cov_last_launch(const cov_handle *h, cov_launch_info *out)
     out->smem_bytes = h->last_info.smem_bytes;
     out->band_rows = h->last_info.band_rows;
     out->planes_in_smem = h->last_info.planes_in_smem;
+    out->multi = h->last_info.multi;
+    out->chunk = h->last_info.chunk;
+    out->max_warps = h->last_info.max_warps;
+    out->plane_mode = h->last_info.plane_mode;
     return COV_OK;
 }
 

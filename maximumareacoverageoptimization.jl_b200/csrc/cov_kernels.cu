@@ -401,6 +401,7 @@ cudaError_t launch_eval(const GridDesc &g, const ObjParams &o, const LaunchCfg &
     cudaError_t err = cudaSuccess; // `counter` is a fresh zeroed slot of the handle's counter ring
     const int N = o.N;
     LaunchInfo li{};
+    li.plane_mode = -1;
     if (cfg.kernel == COV_KERNEL_EXACT) {
         int warps = 8;
         while (warps > 1 && warps * (round_up(3 * N * 8, 16) + round_up(N * 8, 16)) > 96 * 1024) warps /= 2;

@@ -20,6 +20,11 @@ struct LaunchCfg {
 struct LaunchInfo {
     int grid, block, smem_bytes, band_rows, planes_in_smem;
     int kernel; // cov_kernel of the kernel that ran (SPAN = small-swarm, SPAN_GENERAL = CTA per candidate)
+    // template instantiation that ran (names the ncu profile the issue roofline is computed from)
+    int multi;      // 1: several planes / classes / multiplicities
+    int chunk;      // small-swarm kernel: candidates per unit (CHUNK); else 0
+    int max_warps;  // small-swarm kernel: MAXW of the instantiation (20 or 24); else 0
+    int plane_mode; // CTA kernel: 0 lazy, 1 early, 2 staged (PLANES); else -1
 };
 
 // Coverage objective over B candidates (device pointers). counter: one ZEROED unsigned long long

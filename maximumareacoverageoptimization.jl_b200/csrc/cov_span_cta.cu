@@ -340,6 +340,10 @@ cudaError_t launch_span_cta(const GridDesc &g, const ObjParams &o, const LaunchC
         info->band_rows = p.band_rows;
         info->planes_in_smem = mode == kPlanesStaged;
         info->kernel = COV_KERNEL_SPAN_GENERAL;
+        info->multi = multi;
+        info->chunk = 0;
+        info->max_warps = 0;
+        info->plane_mode = mode;
     }
     cudaError_t err;
 #define COV_LAUNCH_CTA(M, E)                                                                                      \

@@ -435,6 +435,10 @@ cudaError_t launch_span_small(const GridDesc &g, const ObjParams &o, const Launc
         info->band_rows = g.ny;
         info->planes_in_smem = 1;
         info->kernel = COV_KERNEL_SPAN;
+        info->multi = multi;
+        info->chunk = chunk;
+        info->max_warps = warps > 20 ? 24 : 20;
+        info->plane_mode = -1;
     }
 #define COV_SMALL_CASE(M, C)                                                                                     \
     case C:                                                                                                      \

@@ -244,6 +244,28 @@ class CoverageEngine:
                                            _ptr(res.get("feasible"))))
         return res
 
+    def eval_batch_best(self, X, barrier: bool = True, out=None):
+        """cov_eval_batch_best: the per-candidate outputs of eval_batch plus the poll winner
+        (best objective, 0-based index; (inf, -1) when the barrier rejects everything), reduced on the device."""
+        X = _f64(X)
+        if X.ndim == 1:
+            X = X.reshape(1, -1)
+        if self.N is None or X.shape[1] != 3 * self.N:
+            raise ValueError("X must be (B, 3N) with the N given to set_params")
+        B = X.shape[0]
+        res = out if out is not None else {}
+        if "obj" not in res:
+            res["obj"] = np.empty(B, dtype=np.float64)
+        if "count" not in res:
+            res["count"] = np.empty(B, dtype=np.int64)
+        if "feasible" not in res:
+            res["feasible"] = np.empty(B, dtype=np.uint8)
+        bo, bi = C.c_double(), C.c_int64()
+        self._check(lib.cov_eval_batch_best(self._h, _ptr(X), B, _ptr(res["obj"]), _ptr(res["count"]),
+                                            _ptr(res["feasible"]), 1 if barrier else 0, C.byref(bo), C.byref(bi)))
+        res["best"] = (bo.value, bi.value)
+        return res
+
     def eval_one(self, x) -> float:
         """AreaMaxObjective(x) for one candidate (src/TDM_STATIC_opt.jl:83-98)."""
         x = _f64(x).ravel()

@@ -9,7 +9,9 @@ import math
 
 import numpy as np
 
-from .engine import TAN_HALF_FOV_DEFAULT
+# This module is deliberately self-contained (NumPy only, no package-relative imports): bench.py's reference arm
+# loads it by file path so that the CPU baseline never touches libcoverage_cuda.
+TAN_HALF_FOV_DEFAULT = math.tan((100 / 180 * math.pi) / 2)  # FOV = 100/180*pi, src/FullSimulation.jl:735 (as engine.py)
 
 GRID_SEED = 20261018
 DOMAIN = 500.0

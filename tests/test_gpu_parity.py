@@ -242,9 +242,9 @@ def test_edge_radii_and_far_centres(cov, orc, engine):
             assert np.array_equal(got["count"], want["count"]), (kernel, got["count"], want["count"])
             assert same_doubles(got["obj"], want["obj"]), (kernel, got["obj"], want["obj"])
             wp = want["progressive"] if which == 0 else np.array([orc.consK_progressive(x, r_max, which) for x in X])
-            # NaN R (row 2), inf - inf (row 10): Julia's max(NaN, 0.0) is NaN and the sums carry it
+            # NaN R of UAV 1 (row 2): Julia's max(NaN, 0.0) is NaN and the sum carries it; UAV 2 alone does not see it
             assert same_doubles(got["progressive"], wp), (kernel, which, got["progressive"], wp)
-            assert np.isnan(wp[2]) == (which in (0, 1)) and np.isnan(wp[10]) == (which in (0, 1))
+            assert np.isnan(wp[2]) == (which in (0, 1)) and wp[3] == (math.inf if which in (0, 1) else 0.0)
         engine.set_option(cov.OPT_PROGRESSIVE_INDEX, 0)
     engine.set_option(cov.OPT_PROGRESSIVE_INDEX, 3)  # UAV 3 of a 2-UAV swarm
     with pytest.raises(cov.CoverageError):
