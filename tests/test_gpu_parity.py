@@ -891,19 +891,48 @@ def test_bench_line_contract(cov):
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "3", "--warmup", "3", "--batch", "50000",
-                        "--cpu-seconds", "0.5"], capture_output=True, text=True, timeout=280, cwd=root)
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "2", "--warmup", "3", "--batch", "50000",
+                        "--launches", "3", "--cpu-seconds", "0.5"], capture_output=True, text=True, timeout=280, cwd=root)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.strip().splitlines() if l.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
-              "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+              "vs_baseline", "dtype", "data", "config", "roofline", "roofline_hbm", "cpu_baseline", "e2e", "e2e_pageable",
+              "gpu_launches", "clocks", "extra_workloads", "h2d_ceiling_gbs"):
         assert k in d, k
-    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["value"] > 0 and d["gpu_launches"] == 3
-    assert d["roofline"]["bound"] == "hbm" and 0 < d["roofline"]["frac"] < 1.5
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["value"] > 0 and d["gpu_launches"] == 2 * 3
+    # the bound that matters is instruction issue; a non-default batch may run an instantiation without a capture
+    assert d["roofline"]["bound"] == "issue" and d["roofline"]["kernel"].startswith("span_small_kernel<")
+    assert d["roofline"]["frac"] is None or 0 < d["roofline"]["frac"] < 1.0
+    assert d["roofline_hbm"]["bound"] == "hbm" and 0 < d["roofline_hbm"]["frac"] < 1.0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["parity_on_sample"] is True
-    assert d["e2e"]["h2d_bytes_per_step"] == 50000 * 120 and d["e2e"]["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 3 * 50000 * 120 and d["e2e"]["value"] > 0 and d["e2e_pageable"]["value"] > 0
+    ex = {e["workload"][:2]: e for e in d["extra_workloads"]}
+    assert set(ex) == {"C3", "C4", "C1"} and all(e["parity_on_sample"] is True for e in ex.values())
+    # the named configs at their bench batch sizes MUST carry a live issue fraction from the committed capture
+    for k in ("C3", "C4"):
+        assert ex[k]["roofline"]["bound"] == "issue" and 0 < ex[k]["roofline"]["frac"] < 1.0, ex[k]["roofline"]
+        assert ex[k]["kernel"].startswith("span_cta_kernel<") and ex[k]["value"] > 0
+    assert ex["C1"]["poll_latency_us"] > 0 and ex["C1"]["mads_solve_ms"] > 0
+
+
+def test_reference_arm_does_not_load_the_product_library():
+    """bench.py --impl reference times the CPU port only: libcoverage_cuda must not even be mapped."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, runpy; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '0'];\n"
+            "try:\n    runpy.run_path(sys.argv[0], run_name='__main__')\nexcept SystemExit:\n    pass\n"
+            "maps = open('/proc/self/maps').read()\n"
+            "print('MAPPED_PRODUCT', 'libcoverage_cuda' in maps, 'MAPPED_ORACLE', 'libcoverage_oracle' in maps)\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=280, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "MAPPED_PRODUCT False MAPPED_ORACLE True" in r.stdout, r.stdout[-500:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    assert d["impl"] == "reference" and d["gpu_launches"] == 0 and d["value"] > 0
 
 
 @pytest.mark.parametrize("n,N,B", [(1024, 50, 100_000), (4096, 200, 4_000)])
