@@ -141,7 +141,7 @@ struct cov_handle {
 
     // cell store
     bool have_grid = false;
-    DevBuf mult, cls, planes;
+    DevBuf mult, cls, planes, planes_q;
     GridDesc g{};
     int64_t n_entries = 0, n_cells = 0;
     int area_exact = 0;
@@ -411,7 +411,7 @@ extern "C" void cov_destroy(cov_handle *h)
     cudaStreamSynchronize(h->stream);
     cudaStreamSynchronize(h->s_in);
     cudaStreamSynchronize(h->s_out);
-    DevBuf *bufs[] = {&h->mult, &h->cls, &h->planes, &h->params, &h->counter, &h->stats, &h->xyT,
+    DevBuf *bufs[] = {&h->mult, &h->cls, &h->planes, &h->planes_q, &h->params, &h->counter, &h->stats, &h->xyT,
                       &h->small_in, &h->argmin_obj, &h->argmin_idx, &h->removed, &h->overflow, &h->dX,
                       &h->d_obj, &h->d_count, &h->d_feas, &h->d_clscnt, &h->d_prog, &h->fire[0], &h->fire[1], &h->fire_p,
                       &h->backup};
@@ -469,7 +469,7 @@ extern "C" int cov_set_option(cov_handle *h, int option, int64_t value)
         h->zero_copy_out = value != 0;
         return COV_OK;
     case COV_OPT_PLANE_MODE:
-        if (value < -1 || value > 2) return fail(h, COV_ERR_INVALID, "plane mode must be -1..2");
+        if (value < -1 || value > 3) return fail(h, COV_ERR_INVALID, "plane mode must be -1..3");
         h->cfg.plane_mode = (int)value;
         return COV_OK;
     case COV_OPT_PROGRESSIVE_INDEX:
@@ -532,6 +532,9 @@ static void describe_lattice(cov_handle *h, int64_t nx, int64_t ny, double dx, d
     g.wpr = (int)((nx + 31) / 32);
     g.stride = g.wpr | 1; // odd: 32 lanes on 32 consecutive rows hit 32 different banks
     g.plane_words = (int)(((int64_t)g.ny * g.stride + 3) / 4 * 4);
+    g.qstride = (g.wpr + 1) & ~1; // even, and an odd number of word pairs (see GridDesc::planes_q)
+    if (((g.qstride >> 1) & 1) == 0) g.qstride += 2;
+    g.planes_q = nullptr;
     g.dx = dx;
     g.dy = dy;
     g.hdx = dx / 2;
@@ -608,6 +611,14 @@ static int rebuild_planes(cov_handle *h, int n_classes, const double *class_weig
     CK(launch_pack_planes((const unsigned char *)h->mult.p, (const unsigned char *)h->cls.p, g,
                           (uint32_t *)h->planes.p, h->stream));
     h->launches += 1;
+    g.planes_q = nullptr;
+    if (np == 1) { // the sweep mode of the CTA kernel reads plane 0 in its own aligned, swizzled layout
+        OK(ensure(h, h->planes_q, ((size_t)g.ny * g.qstride + 8) * 4));
+        CK(cudaMemsetAsync(h->planes_q.p, 0, ((size_t)g.ny * g.qstride + 8) * 4, h->stream));
+        CK(launch_requad_plane(g, (uint32_t *)h->planes_q.p, h->stream));
+        h->launches += 1;
+        g.planes_q = (const uint32_t *)h->planes_q.p;
+    }
     // area_exact: every partial sum of the reference's list-order Float64 accumulation is an
     // integer multiple of a common power of two and stays below 2^53 of them, hence exact in any
     // order, and so is sum_k fl(w_k * count_k).

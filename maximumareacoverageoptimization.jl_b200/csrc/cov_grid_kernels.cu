@@ -93,6 +93,24 @@ cudaError_t launch_pack_planes(const unsigned char *mult, const unsigned char *c
     return cudaGetLastError();
 }
 
+__global__ void requad_plane_kernel(const __grid_constant__ GridDesc g, uint32_t *__restrict__ q)
+{
+    const long long n = (long long)g.ny * g.qstride;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const int row = (int)(t / g.qstride), w = (int)(t % g.qstride);
+        const int src = w ^ ((row >> 4) & 1); // row = j - 1; the swizzle is an involution within a word pair
+        q[t] = src < g.wpr ? g.planes[(size_t)row * g.stride + src] : 0u;
+    }
+}
+cudaError_t launch_requad_plane(const GridDesc &g, uint32_t *planes_q, cudaStream_t s)
+{
+    const long long n = (long long)g.ny * g.qstride;
+    const int block = 256;
+    const int grid = (int)std::min<long long>((n + block - 1) / block, 148 * 8);
+    requad_plane_kernel<<<max(grid, 1), block, 0, s>>>(g, planes_q);
+    return cudaGetLastError();
+}
+
 __global__ void fill_full_kernel(unsigned char *mult, unsigned char *cls, long long ncell)
 {
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < ncell;

@@ -51,6 +51,8 @@ cudaError_t launch_grid_stats(const unsigned char *mult, const unsigned char *cl
                               unsigned long long *stats, cudaStream_t s);
 cudaError_t launch_pack_planes(const unsigned char *mult, const unsigned char *cls, const GridDesc &g,
                                uint32_t *planes, cudaStream_t s);
+// plane 0 in the pair-aligned, swizzled layout of the CTA kernel's sweep mode (GridDesc::planes_q)
+cudaError_t launch_requad_plane(const GridDesc &g, uint32_t *planes_q, cudaStream_t s);
 cudaError_t launch_fill_full(unsigned char *mult, unsigned char *cls, long long ncell, cudaStream_t s);
 cudaError_t launch_bits_to_cells(const uint32_t *bits, int nx, int ny, unsigned char *mult,
                                  unsigned char *cls, cudaStream_t s);

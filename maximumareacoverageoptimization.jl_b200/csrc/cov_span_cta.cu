@@ -37,18 +37,27 @@ struct CtaPlan {
     int fixed_bytes, tab_bytes, fb_bytes, plane_bytes, band_rows, total_bytes, ctas_per_sm;
 };
 // how the kernel reads the fire words
-enum { kPlanesLazy = 0, kPlanesEarly = 1, kPlanesStaged = 2 };
+// kPlanesSweep: PAINT THEN SWEEP.  The spans are only painted -- the two edge words of a span with result-less
+// atomicOr, the whole words in between with plain (paired, 64-bit) stores of all-ones -- and nothing is counted
+// while painting; once the band is painted, all threads sweep it linearly with 128-bit loads:
+// count += popc(framebuffer & fire plane), framebuffer = 0.  A covered cell is counted once however many discs
+// cover it, the paint loop has no dependent atomic -> popc chain, and a word painted by k discs costs k cheap
+// stores plus one sweep visit instead of k atomics with return values.  Framebuffer band and staged plane band
+// share the layout of GridDesc::planes_q, so the sweep needs no row / column arithmetic at all.
+enum { kPlanesLazy = 0, kPlanesEarly = 1, kPlanesStaged = 2, kPlanesSweep = 3 };
 // unit table: one 32-bit entry (disc << 16 | unit within the disc) per 32-row work unit of a band
 __host__ __device__ inline int cta_tab_bytes(int N, int band_rows) { return round_up(N * ((band_rows + 31) / 32) * 4, 16); }
 __host__ __device__ inline int cta_fixed_bytes(int N)
 {
     return round_up(3 * N * 8, 16) + N * 32 + round_up((N + 1) * 4, 16) + 1024;
 }
-static CtaPlan cta_plan(const GridDesc &g, int N, int smem_per_sm, int band_rows_opt, int ctas_opt, bool staged)
+static CtaPlan cta_plan(const GridDesc &g, int N, int smem_per_sm, int band_rows_opt, int ctas_opt, bool staged,
+                        bool sweep = false)
 {
     CtaPlan p{};
     p.fixed_bytes = cta_fixed_bytes(N) + (staged ? 32 : 0); // + the band's plane rows and an mbarrier when staged
-    const int row_bytes = g.stride * 4 * (staged ? 2 : 1);
+    const int fstride = sweep ? g.qstride : g.stride;
+    const int row_bytes = fstride * 4 * (staged ? 2 : 1);
     // as many co-resident CTAs as possible (they overlap each other's serial phases), as long as a
     // band still holds a useful number of rows
     int best = 0;
@@ -58,7 +67,7 @@ static CtaPlan cta_plan(const GridDesc &g, int N, int smem_per_sm, int band_rows
         if (rows > g.ny) rows = g.ny;
         if (staged && rows < g.ny) rows &= ~3; // bands start on 16-byte boundaries of the plane
         while (rows > 1 && p.fixed_bytes + cta_tab_bytes(N, rows) + round_up(rows * row_bytes, 16) + 32 > budget) rows -= staged ? 4 : 1;
-        if (rows >= std::min(g.ny, 96) || ctas == 1) {
+        if (rows >= std::min(g.ny, 80) || ctas == 1) {
             best = ctas;
             p.band_rows = rows;
             break;
@@ -66,11 +75,42 @@ static CtaPlan cta_plan(const GridDesc &g, int N, int smem_per_sm, int band_rows
     }
     p.ctas_per_sm = best;
     if (band_rows_opt > 0 && band_rows_opt < p.band_rows) p.band_rows = staged ? std::max(4, band_rows_opt & ~3) : band_rows_opt;
-    p.fb_bytes = p.band_rows > 0 ? round_up(p.band_rows * g.stride * 4, 16) : 0;
-    p.plane_bytes = staged && p.band_rows > 0 ? round_up(p.band_rows * g.stride * 4, 16) + 16 : 0;
+    p.fb_bytes = p.band_rows > 0 ? round_up(p.band_rows * fstride * 4, 16) : 0;
+    p.plane_bytes = staged && p.band_rows > 0 ? round_up(p.band_rows * fstride * 4, 16) + 16 : 0;
     p.tab_bytes = p.band_rows > 0 ? cta_tab_bytes(N, p.band_rows) : 0;
     p.total_bytes = p.fixed_bytes + p.tab_bytes + p.fb_bytes + p.plane_bytes;
     return p;
+}
+
+// Sweep mode: paint columns [lo, hi] of grid row j (1-based) into the band framebuffer (row 0 = grid row jb0),
+// nothing else.  Edge words by atomicOr without a return value; whole words in between by plain stores of
+// all-ones, in aligned pairs where possible (every writer of such a word writes the same value, and an atomicOr
+// that meets the store on the same word leaves all-ones whichever comes first).
+__device__ __forceinline__ void paint_only(uint32_t *fb, int qstride, int jb0, int j, int lo, int hi, bool valid)
+{
+    const int a = lo - 1, b = hi - 1;
+    const int wa = a >> 5, wb = b >> 5;
+    uint32_t *row = fb + (j - jb0) * qstride;
+    const int sw = ((j - 1) >> 4) & 1;
+    const uint32_t ma = 0xffffffffu << (a & 31), mb = 0xffffffffu >> (31 - (b & 31));
+    COV_ASSERT(!valid || (lo >= 1 && lo <= hi && j >= jb0));
+    if (!valid) return;
+    if (wa == wb) {
+        atomicOr(row + (wa ^ sw), ma & mb);
+        return;
+    }
+    atomicOr(row + (wa ^ sw), ma);
+    atomicOr(row + (wb ^ sw), mb);
+    int s = wa + 1, e = wb; // whole words [s, e)
+    if (s < e && (s & 1)) {
+        row[s ^ sw] = 0xffffffffu;
+        ++s;
+    }
+    if (s < e && (e & 1)) {
+        --e;
+        row[e ^ sw] = 0xffffffffu;
+    }
+    for (; s < e; s += 2) *reinterpret_cast<uint2 *>(row + s) = make_uint2(0xffffffffu, 0xffffffffu);
 }
 
 template <bool MULTI, int PLANES>
@@ -103,7 +143,9 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
     uint32_t *plane_s = fb + fb_bytes / 4;
     uint64_t *bar = reinterpret_cast<uint64_t *>(plane_s + fb_bytes / 4);
     uint32_t bar_phase = 0;
-    if (PLANES == kPlanesStaged && tid == 0) {
+    constexpr bool kTma = PLANES == kPlanesStaged || PLANES == kPlanesSweep; // the band's plane rows come by TMA
+    const int fstride = PLANES == kPlanesSweep ? g.qstride : g.stride;          // words per framebuffer row
+    if (kTma && tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -182,12 +224,13 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
         // ---- D. bands of framebuffer rows ----
         for (int jb0 = 1; jb0 <= g.ny; jb0 += band_rows) {
             const int jb1 = min(g.ny, jb0 + band_rows - 1);
-            if (PLANES == kPlanesStaged && tid == 32) {
+            if (kTma && tid == 32) {
                 // rows jb0..jb1 of the plane are contiguous; (jb0 - 1) * stride is a multiple of 4 words
-                const uint32_t words = (uint32_t)round_up((jb1 - jb0 + 1) * g.stride, 4);
+                const uint32_t words = (uint32_t)round_up((jb1 - jb0 + 1) * fstride, 4);
+                const uint32_t *src = PLANES == kPlanesSweep ? g.planes_q : g.planes;
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // earlier generic reads of plane_s
                 mbar_expect_tx(bar, words * 4);
-                bulk_g2s(plane_s, g.planes + (size_t)(jb0 - 1) * g.stride, words * 4, bar);
+                bulk_g2s(plane_s, src + (size_t)(jb0 - 1) * fstride, words * 4, bar);
             }
             // work units = 32-row blocks of a disc's rows inside the band; unit_tab[u] = (disc, unit within the
             // disc).  All warps take part: 256 discs per pass, warp-level scans chained through shared memory.
@@ -268,12 +311,34 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
                         lo1 = l2;
                         hi1 = h2;
                     }
-                    paint_span<MULTI, PLANES == kPlanesStaged, true, PLANES == kPlanesEarly>(g, fb, planes_eff, jj0, lo0, hi0, st0 == kSpan, true, cnt, jb0);
-                    paint_span<MULTI, PLANES == kPlanesStaged, true, PLANES == kPlanesEarly>(g, fb, planes_eff, jj1, lo1, hi1, st1 == kSpan, true, cnt, jb0);
+                    if (PLANES == kPlanesSweep) {
+                        paint_only(fb, fstride, jb0, jj0, lo0, hi0, st0 == kSpan);
+                        paint_only(fb, fstride, jb0, jj1, lo1, hi1, st1 == kSpan);
+                    } else {
+                        paint_span<MULTI, PLANES == kPlanesStaged, true, PLANES == kPlanesEarly>(g, fb, planes_eff, jj0, lo0, hi0, st0 == kSpan, true, cnt, jb0);
+                        paint_span<MULTI, PLANES == kPlanesStaged, true, PLANES == kPlanesEarly>(g, fb, planes_eff, jj1, lo1, hi1, st1 == kSpan, true, cnt, jb0);
+                    }
                 }
             }
             __syncthreads();
-            if (units != 0) {
+            if (PLANES == kPlanesSweep) {
+                mbar_wait(bar, bar_phase); // the band's plane rows (in flight since the band began)
+                bar_phase ^= 1u;
+                if (units != 0) {
+                    // count and clear in one linear pass: framebuffer and plane band have the same layout
+                    const int used = (jb1 - jb0 + 1) * fstride;
+                    uint4 *f4 = reinterpret_cast<uint4 *>(fb);
+                    const uint4 *p4 = reinterpret_cast<const uint4 *>(plane_s);
+                    uint32_t c = 0;
+                    for (int t = tid; t < (used + 3) / 4; t += kCtaThreads) {
+                        const uint4 f = f4[t], pl = p4[t];
+                        c += __popc(f.x & pl.x) + __popc(f.y & pl.y) + __popc(f.z & pl.z) + __popc(f.w & pl.w);
+                        f4[t] = make_uint4(0, 0, 0, 0);
+                    }
+                    cnt[0] += c;
+                }
+                __syncthreads(); // plane_s is overwritten by the next band's copy, issued right away
+            } else if (units != 0) {
                 // clear the band for the next band / candidate
                 const int used = (jb1 - jb0 + 1) * g.stride;
                 for (int t = tid; t < (used + 3) / 4; t += kCtaThreads)
@@ -325,9 +390,10 @@ cudaError_t launch_span_cta(const GridDesc &g, const ObjParams &o, const LaunchC
     // (measured, B200: staging wins from a few dozen discs per candidate on -- C3 +6 %, C4 +27 % -- and loses
     // for a handful of discs on a big grid, where most of a staged band is never looked at)
     int mode = multi ? kPlanesLazy : (cfg.plane_mode >= 0 ? cfg.plane_mode : (o.N >= 16 ? kPlanesStaged : kPlanesEarly));
-    if (multi) mode = kPlanesLazy;
-    CtaPlan p = cta_plan(g, o.N, cfg.max_smem_optin + 1024, cfg.band_rows, cfg.ctas_per_sm, mode == kPlanesStaged);
-    if (mode == kPlanesStaged && p.band_rows < 4) {
+    if (multi || (mode == kPlanesSweep && !g.planes_q)) mode = kPlanesLazy;
+    CtaPlan p = cta_plan(g, o.N, cfg.max_smem_optin + 1024, cfg.band_rows, cfg.ctas_per_sm,
+                         mode == kPlanesStaged || mode == kPlanesSweep, mode == kPlanesSweep);
+    if ((mode == kPlanesStaged || mode == kPlanesSweep) && p.band_rows < 4) {
         mode = o.N <= 96 ? kPlanesEarly : kPlanesLazy;
         p = cta_plan(g, o.N, cfg.max_smem_optin + 1024, cfg.band_rows, cfg.ctas_per_sm, false);
     }
@@ -338,7 +404,7 @@ cudaError_t launch_span_cta(const GridDesc &g, const ObjParams &o, const LaunchC
         info->block = kCtaThreads;
         info->smem_bytes = p.total_bytes;
         info->band_rows = p.band_rows;
-        info->planes_in_smem = mode == kPlanesStaged;
+        info->planes_in_smem = mode == kPlanesStaged || mode == kPlanesSweep;
         info->kernel = COV_KERNEL_SPAN_GENERAL;
         info->multi = multi;
         info->chunk = 0;
@@ -356,6 +422,7 @@ cudaError_t launch_span_cta(const GridDesc &g, const ObjParams &o, const LaunchC
                                                                             p.fb_bytes);                          \
     } while (0)
     if (multi) COV_LAUNCH_CTA(true, kPlanesLazy);
+    else if (mode == kPlanesSweep) COV_LAUNCH_CTA(false, kPlanesSweep);
     else if (mode == kPlanesStaged) COV_LAUNCH_CTA(false, kPlanesStaged);
     else if (mode == kPlanesEarly) COV_LAUNCH_CTA(false, kPlanesEarly);
     else COV_LAUNCH_CTA(false, kPlanesLazy);

@@ -32,6 +32,12 @@ struct GridDesc {
     int plane_mult[kMaxPlanes];      // 1, 2, 4, ... entries per set bit
     double class_weight[kMaxClasses];
     const uint32_t *planes;          // device: n_planes * plane_words
+    // Plane 0 once more for the paint-then-sweep mode of the CTA kernel (single-plane stores only, else null):
+    // rows of `qstride` words, qstride even and qstride/2 odd (rows are 8-byte aligned, 16 consecutive rows start
+    // in 16 different bank pairs), and word w of grid row j stored at w ^ (((j-1) >> 4) & 1): 32 lanes on 32
+    // consecutive rows at one column hit 32 different banks although the rows are aligned.
+    int qstride;
+    const uint32_t *planes_q;        // device: ny * qstride words (+ padding), or null
 };
 
 // Captured variables of the reference's closures (createObjective, create_cons3, cons7, cons8).
