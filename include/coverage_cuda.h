@@ -59,7 +59,10 @@ enum {
     COV_KERNEL_SPAN = 1,    /* row-span kernels, small-swarm variant whenever it applies (from 128 candidates on) */
     COV_KERNEL_BRUTE = 2,   /* every cell against every disc, FP32 band + FP64 exact band cells */
     COV_KERNEL_EXACT = 3,   /* every cell against every disc in FP64 only (slow cross-check) */
-    COV_KERNEL_SPAN_GENERAL = 4 /* force the general span kernel (one CTA per candidate, any N) */
+    COV_KERNEL_SPAN_GENERAL = 4, /* force the general span kernel (one CTA per candidate, any N) */
+    COV_KERNEL_ORDERED = 5  /* the reference's own loop over the point list in list order, FP64 only: the Float64 area is
+                               the reference's whatever the weights. Chosen automatically (whatever this option says)
+                               when cov_grid_info.area_exact == 0; selectable as a cross-check otherwise */
 };
 
 enum {
@@ -72,7 +75,8 @@ enum {
     COV_OPT_TRACE = 7,          /* 1: record a per-slice device timeline of every host-path call (cov_get_trace) */
     COV_OPT_PLANE_MODE = 9,     /* CTA kernel, how fire words are read: -1 auto (default), 0 through L2 only when
                                    the framebuffer atomic left new bits, 1 through L2 ahead of the atomics,
-                                   2 staged in shared memory band by band with TMA bulk copies */
+                                   2 staged in shared memory band by band with TMA bulk copies, 3 paint-then-sweep
+                                   (spans only painted, then popc(framebuffer & staged plane) over the band) */
     COV_OPT_ZEROCOPY_OUT = 8,   /* 1 (default): the host path's kernels write their results straight into pinned host
                                    memory; 0: into device buffers, copied back slice by slice */
     COV_OPT_PROGRESSIVE_INDEX = 10 /* which progressive constraint the `progressive` output of cov_eval_batch_ex is:

@@ -145,25 +145,22 @@ class ResidentList:
         eng = self.sync()
         circles = np.ascontiguousarray(circles, dtype=np.float64).ravel()
         n = circles.size // 3
-        if eng.N != n:
+        # the objective with the penalty switched off is -area exactly: -area + violation * 0.0 (finite radii; a
+        # non-finite radius makes the product NaN, as it makes the reference's own objective)
+        if eng.N != n or eng.param_owner != ("calculateArea", n):
             eng.set_params(n, np.zeros(n), penalty_scale=0.0)
-        info = eng.grid_info()
-        if info["area_exact"]:
-            res = eng.eval_batch(circles.reshape(1, -1), want_feasible=False, want_class_count=True)
-            cc = res["class_count"][0]
-            # the DEVICE's class numbering: fixed when the store was created, it does not follow removals
-            # (the host list's order of first appearance does)
-            w = eng.class_weights()
-            area = 0.0
-            for k in range(info["n_classes"]):
-                area += w[k] * float(cc[k])  # every term and partial sum exact (area_exact)
-            return area, int(res["count"][0])
-        # Non-dyadic weights: the Float64 result depends on the list order of the additions.
-        # The device decides coverage per cell; the ordered sum is replayed here.
-        covered = eng.covered_mask(circles)[self.cell_index()].astype(bool)
+            eng.param_owner = ("calculateArea", n)
+        res = eng.eval_batch(circles.reshape(1, -1), want_feasible=False)
+        # dyadic weights: sum_k w_k * count_k in any order; otherwise the library replays the reference's list-order
+        # sum on the device (ordered kernel) -- either way this is calculateArea's Float64
+        area = 0.0 - float(res["obj"][0])
+        return (area if area == area else self._area_on_host(circles)), int(res["count"][0])
+
+    def _area_on_host(self, circles) -> float:
+        """Non-finite radii only: replay the ordered sum from the device's covered mask."""
+        covered = self.engine.covered_mask(circles)[self.cell_index()].astype(bool)
         w = self.points.data[covered, 3]
-        area = float(np.cumsum(w)[-1]) if w.size else 0.0  # cumsum: strictly sequential
-        return area, int(covered.sum())
+        return float(np.cumsum(w)[-1]) if w.size else 0.0  # cumsum: strictly sequential
 
 
 _resident_cache: dict[int, ResidentList] = {}

@@ -49,12 +49,10 @@ class AreaMaxObjective:
 
     def native_solver(self, constraints):
         """A callable (x0, n_iter, granularity, seed) -> (x, objective, stats) running cov_mads_solve with these
-        extreme constraints fused, or None when a constraint cannot be fused or the area is order-dependent."""
+        extreme constraints fused, or None when a constraint cannot be fused."""
         if self.fuse(constraints):
             return None
         res, eng = self._engine()
-        if not eng.grid_info()["area_exact"]:
-            return None
         return eng.mads_solve
 
     def _engine(self):
@@ -75,30 +73,16 @@ class AreaMaxObjective:
         constraints' verdicts."""
         res, eng = self._engine()
         X = np.ascontiguousarray(X, dtype=np.float64).reshape(-1, 3 * self.N)
-        info = eng.grid_info()
-        if not info["area_exact"]:
-            # order-dependent Float64 sum (non-dyadic weights): per-candidate replay
-            obj = np.array([self._replay(res, x) for x in X])
-            if want_feasible:
-                return obj, eng.eval_batch(X, want_count=False)["feasible"].astype(bool)
-            return obj
+        # (non-dyadic weights, where the Float64 sum depends on the list order, are replayed in list order on the
+        # device by the library's ordered kernel: nothing special here)
         out = eng.eval_batch(X, want_count=False, want_feasible=want_feasible)
         if want_feasible:
             return out["obj"], out["feasible"].astype(bool)
         return out["obj"]
 
-    def _replay(self, res, x):
-        area, _ = res.area_and_count(x)
-        violation = 0.0
-        for i in range(self.N):
-            violation += abs(float(x[i + 2 * self.N]) - float(self.r_max[i]))
-        return -area + violation * 1e5
-
     def __call__(self, x) -> float:
         res, eng = self._engine()
         x = np.ascontiguousarray(x, dtype=np.float64).ravel()
-        if not eng.grid_info()["area_exact"]:
-            return self._replay(res, x)
         return eng.eval_one(x)
 
 

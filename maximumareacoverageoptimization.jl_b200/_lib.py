@@ -20,7 +20,7 @@ COV_ERR_OFF_LATTICE = -4
 COV_ERR_LIMIT = -5
 COV_ERR_NOMEM = -6
 
-KERNEL_AUTO, KERNEL_SPAN, KERNEL_BRUTE, KERNEL_EXACT, KERNEL_SPAN_GENERAL = 0, 1, 2, 3, 4
+KERNEL_AUTO, KERNEL_SPAN, KERNEL_BRUTE, KERNEL_EXACT, KERNEL_SPAN_GENERAL, KERNEL_ORDERED = 0, 1, 2, 3, 4, 5
 OPT_KERNEL, OPT_WARPS_PER_CTA, OPT_CTAS_PER_SM, OPT_BAND_ROWS, OPT_FORCE_EXACT, OPT_CHUNK, OPT_TRACE, OPT_ZEROCOPY_OUT, OPT_PLANE_MODE = 1, 2, 3, 4, 5, 6, 7, 8, 9
 OPT_PROGRESSIVE_INDEX = 10
 

@@ -145,6 +145,14 @@ struct cov_handle {
     GridDesc g{};
     int64_t n_entries = 0, n_cells = 0;
     int area_exact = 0;
+    // The point list in the reference's order, for the ordered kernel (area_exact == 0 or COV_KERNEL_ORDERED).
+    // ent_known: the host mirror follows the order cov_set_points / cov_add_points gave (removals pending in
+    // ent_removed_pending are applied lazily: every entry of a covered cell goes, the others keep their order);
+    // otherwise the order is createPOI's (i outer, j inner, duplicates together), built from the cell store on demand.
+    std::vector<int> ent_cell_h;
+    std::vector<unsigned char> ent_cls_h;
+    bool ent_known = false, ent_removed_pending = false, ent_dev_valid = false;
+    DevBuf ent_cell, ent_cls;
 
     // closure parameters
     bool have_params = false;
@@ -414,7 +422,7 @@ extern "C" void cov_destroy(cov_handle *h)
     DevBuf *bufs[] = {&h->mult, &h->cls, &h->planes, &h->planes_q, &h->params, &h->counter, &h->stats, &h->xyT,
                       &h->small_in, &h->argmin_obj, &h->argmin_idx, &h->removed, &h->overflow, &h->dX,
                       &h->d_obj, &h->d_count, &h->d_feas, &h->d_clscnt, &h->d_prog, &h->fire[0], &h->fire[1], &h->fire_p,
-                      &h->backup};
+                      &h->backup, &h->ent_cell, &h->ent_cls};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (int k = 0; k < 2; ++k)
@@ -440,7 +448,7 @@ extern "C" int cov_set_option(cov_handle *h, int option, int64_t value)
     if (!h) return fail(nullptr, COV_ERR_INVALID, "cov_set_option: NULL handle");
     switch (option) {
     case COV_OPT_KERNEL:
-        if (value < COV_KERNEL_AUTO || value > COV_KERNEL_SPAN_GENERAL) return fail(h, COV_ERR_INVALID, "unknown kernel id");
+        if (value < COV_KERNEL_AUTO || value > COV_KERNEL_ORDERED) return fail(h, COV_ERR_INVALID, "unknown kernel id");
         h->cfg.kernel = (int)value;
         return COV_OK;
     case COV_OPT_WARPS_PER_CTA:
@@ -549,6 +557,7 @@ static void describe_lattice(cov_handle *h, int64_t nx, int64_t ny, double dx, d
     g.inv_dyf = (float)g.inv_dy;
     g.extent = (float)std::max((double)nx * dx, (double)ny * dy);
     g.extent = std::nextafter(g.extent, INFINITY);
+    g.k_ca = std::nextafter((float)(0.75 * g.inv_dx * 1.000001), INFINITY);
     g.lattice_f32_exact = f32_exact(dx) && f32_exact(dy) && f32_exact(g.hdx) && f32_exact(g.hdy) &&
                           f32_exact((double)nx * dx) && f32_exact((double)ny * dy);
 }
@@ -663,6 +672,88 @@ static int alloc_cells(cov_handle *h)
     return COV_OK;
 }
 
+// ---- the ordered point list ------------------------------------------------------------------------------
+static void entries_forget(cov_handle *h) // the store was re-created without a list: order = createPOI's, on demand
+{
+    h->ent_known = false;
+    h->ent_removed_pending = false;
+    h->ent_dev_valid = false;
+    h->ent_cell_h.clear();
+    h->ent_cls_h.clear();
+    h->g.ent_cell = nullptr;
+    h->g.ent_cls = nullptr;
+    h->g.n_ent = 0;
+}
+// rmvCoveredPOI deletes every entry of a covered cell and keeps the order of the rest
+// (src/CellFunctions.jl:81-108): drop the mirror's entries whose cell is now empty.
+static int entries_apply_removals(cov_handle *h)
+{
+    if (!h->ent_known || !h->ent_removed_pending) return COV_OK;
+    const size_t ncell = (size_t)h->g.nx * h->g.ny;
+    std::vector<unsigned char> m(ncell);
+    CK(cudaMemcpyAsync(m.data(), h->mult.p, ncell, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    size_t keep = 0;
+    for (size_t p = 0; p < h->ent_cell_h.size(); ++p)
+        if (m[(size_t)h->ent_cell_h[p]]) {
+            h->ent_cell_h[keep] = h->ent_cell_h[p];
+            h->ent_cls_h[keep] = h->ent_cls_h[p];
+            ++keep;
+        }
+    h->ent_cell_h.resize(keep);
+    h->ent_cls_h.resize(keep);
+    h->ent_removed_pending = false;
+    h->ent_dev_valid = false;
+    return COV_OK;
+}
+// Make g.ent_cell / g.ent_cls / g.n_ent describe the current list on the device.
+static int entries_on_device(cov_handle *h)
+{
+    if (h->ent_dev_valid) return COV_OK;
+    OK(entries_apply_removals(h));
+    if (!h->ent_known) {
+        // no list was ever given (bit grid, cell bytes, createPOI, automaton): createPOI's order,
+        // i outer and j inner (src/AreaCoverageCalculation.jl:14-15), the entries of a cell together
+        const size_t ncell = (size_t)h->g.nx * h->g.ny;
+        std::vector<unsigned char> m(ncell), k(ncell);
+        CK(cudaMemcpyAsync(m.data(), h->mult.p, ncell, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(k.data(), h->cls.p, ncell, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        h->ent_cell_h.clear();
+        h->ent_cls_h.clear();
+        for (int i = 0; i < h->g.nx; ++i)
+            for (int j = 0; j < h->g.ny; ++j) {
+                const size_t cell = (size_t)i + (size_t)h->g.nx * j;
+                for (unsigned r = 0; r < m[cell]; ++r) {
+                    h->ent_cell_h.push_back((int)cell);
+                    h->ent_cls_h.push_back((unsigned char)(k[cell] & (kMaxClasses - 1)));
+                }
+            }
+    }
+    const size_t P = h->ent_cell_h.size();
+    if ((int64_t)P != h->n_entries)
+        return fail(h, COV_ERR_STATE, "internal: the ordered point list disagrees with the cell store (" +
+                                          std::to_string(P) + " vs " + std::to_string(h->n_entries) + " entries)");
+    OK(ensure(h, h->ent_cell, std::max<size_t>(P, 1) * sizeof(int)));
+    OK(ensure(h, h->ent_cls, std::max<size_t>(P, 1)));
+    if (P) {
+        CK(cudaMemcpyAsync(h->ent_cell.p, h->ent_cell_h.data(), P * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->ent_cls.p, h->ent_cls_h.data(), P, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream)); // pageable sources
+    }
+    if (!h->ent_known) { // the canonical list is cheap to rebuild and can be large: do not keep it
+        h->ent_cell_h.clear();
+        h->ent_cell_h.shrink_to_fit();
+        h->ent_cls_h.clear();
+        h->ent_cls_h.shrink_to_fit();
+    }
+    h->g.ent_cell = (const int *)h->ent_cell.p;
+    h->g.ent_cls = (const unsigned char *)h->ent_cls.p;
+    h->g.n_ent = (long long)P;
+    h->ent_dev_valid = true;
+    return COV_OK;
+}
+
 // An append (cov_add_points, cov_fire_step) can fail half-way: a multiplicity overflowing 255 or entries of
 // different weights on one cell are found by the kernel that is already writing.  The store is snapshot
 // before and put back on failure, so that mult/cls, the bit planes and n_entries never disagree.
@@ -695,6 +786,7 @@ extern "C" int cov_set_grid_bits(cov_handle *h, int64_t nx, int64_t ny, double d
     OK(check_lattice(h, nx, ny, dx, dy));
     h->have_grid = false;
     h->have_fire = false; // the automaton's state belongs to the lattice it was initialised on
+    entries_forget(h);
     describe_lattice(h, nx, ny, dx, dy);
     OK(alloc_cells(h));
     const size_t words = (size_t)ny * ((nx + 31) / 32);
@@ -727,6 +819,7 @@ extern "C" int cov_set_grid_cells(cov_handle *h, int64_t nx, int64_t ny, double 
             if (cls[t] >= n_classes) return fail(h, COV_ERR_INVALID, "cov_set_grid_cells: class index out of range");
     h->have_grid = false;
     h->have_fire = false; // the automaton's state belongs to the lattice it was initialised on
+    entries_forget(h);
     describe_lattice(h, nx, ny, dx, dy);
     OK(alloc_cells(h));
     CK(cudaMemcpyAsync(h->mult.p, mult, ncell, cudaMemcpyHostToDevice, h->stream));
@@ -745,6 +838,7 @@ extern "C" int cov_set_grid_full(cov_handle *h, int64_t nx, int64_t ny, double d
     OK(check_lattice(h, nx, ny, dx, dy));
     h->have_grid = false;
     h->have_fire = false; // the automaton's state belongs to the lattice it was initialised on
+    entries_forget(h);
     describe_lattice(h, nx, ny, dx, dy);
     OK(alloc_cells(h));
     CK(launch_fill_full((unsigned char *)h->mult.p, (unsigned char *)h->cls.p, (long long)nx * ny, h->stream));
@@ -833,6 +927,7 @@ extern "C" int cov_set_points(cov_handle *h, const double *pts5, int64_t P, int6
     OK(check_lattice(h, nx, ny, dx, dy));
     h->have_grid = false;
     h->have_fire = false; // the automaton's state belongs to the lattice it was initialised on
+    entries_forget(h);
     describe_lattice(h, nx, ny, dx, dy);
     std::vector<int> cell;
     std::vector<unsigned char> pcls;
@@ -848,6 +943,9 @@ extern "C" int cov_set_points(cov_handle *h, const double *pts5, int64_t P, int6
     CK(cudaMemsetAsync(h->mult.p, 0, ncell + 4, h->stream));
     CK(cudaMemsetAsync(h->cls.p, 0xff, ncell + 4, h->stream));
     OK(upload_points(h, cell, pcls));
+    h->ent_cell_h = cell; // the list order of the reference's points_of_interest
+    h->ent_cls_h = pcls;
+    h->ent_known = true;
     return rebuild_planes(h, n_classes, cw);
 }
 
@@ -868,6 +966,7 @@ extern "C" int cov_add_points(cov_handle *h, const double *pts5, int64_t P)
         n_classes = 1;
         cw[0] = h->g.class_weight[0];
     }
+    OK(entries_apply_removals(h)); // before new entries can land on cells that a removal emptied
     OK(snapshot_cells(h));
     const int rc = upload_points(h, cell, pcls);
     if (rc != COV_OK) { // nothing was appended: the store, its planes and its counts stay as they were
@@ -876,6 +975,11 @@ extern "C" int cov_add_points(cov_handle *h, const double *pts5, int64_t P)
         h->err = msg;
         return rc;
     }
+    if (h->ent_known) { // push! appends at the end (src/CellFunctions.jl:74)
+        h->ent_cell_h.insert(h->ent_cell_h.end(), cell.begin(), cell.end());
+        h->ent_cls_h.insert(h->ent_cls_h.end(), pcls.begin(), pcls.end());
+    }
+    h->ent_dev_valid = false;
     return rebuild_planes(h, n_classes, cw);
 }
 
@@ -941,6 +1045,10 @@ extern "C" int cov_remove_covered(cov_handle *h, const double *xyR, int64_t N, i
     CK(cudaMemcpyAsync(hr, h->removed.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (removed) *removed = (int64_t)*hr;
+    if (*hr) {
+        h->ent_removed_pending = h->ent_known;
+        h->ent_dev_valid = false;
+    }
     double cw[kMaxClasses];
     for (int k = 0; k < kMaxClasses; ++k) cw[k] = h->g.class_weight[k];
     return rebuild_planes(h, h->g.n_classes, cw);
@@ -981,6 +1089,7 @@ extern "C" int cov_fire_init(cov_handle *h, int64_t nx, int64_t ny, double dx, d
         if (state[t] > 2) return fail(h, COV_ERR_INVALID, "cov_fire_init: cell states must be 0 (empty), 1 (tree), 2 (fire)");
     h->have_grid = false;
     h->have_fire = false;
+    entries_forget(h);
     describe_lattice(h, nx, ny, dx, dy);
     OK(alloc_cells(h));
     OK(ensure(h, h->fire[0], ncell));
@@ -1039,6 +1148,7 @@ extern "C" int cov_fire_step(cov_handle *h, double wind_speed, double wind_direc
     h->fire_cur = cur ^ 1;
     if (n_pushed) *n_pushed = (int64_t)*hr;
     if (!append || *hr == 0) return COV_OK;
+    entries_forget(h); // the automaton pushes in cell order; from here on the list order is createPOI's
     double cw[kMaxClasses];
     for (int k = 0; k < kMaxClasses; ++k) cw[k] = h->g.class_weight[k];
     return rebuild_planes(h, 1, cw);
@@ -1108,6 +1218,8 @@ extern "C" int cov_set_params(cov_handle *h, int64_t N, const double *r_max, dou
 // ------------------------------------------------------------------------------------------
 static int launch_on_main(cov_handle *h, const double *dX, int64_t B, const EvalOut &out, bool timed)
 {
+    h->cfg.ordered = h->area_exact ? 0 : 1; // non-dyadic weights: the sum is replayed in list order
+    if (h->cfg.ordered || h->cfg.kernel == COV_KERNEL_ORDERED) OK(entries_on_device(h));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (timed) {
         e0 = get_event(h);

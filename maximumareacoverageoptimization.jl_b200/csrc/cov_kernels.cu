@@ -385,6 +385,83 @@ exact_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjPara
 }
 
 // ------------------------------------------------------------------------------------------
+// ordered kernel: the reference's own loop (src/AreaCoverageCalculation.jl:63-110) over the point LIST --
+// for each entry in list order, the first covering disc adds the entry's weight to a Float64 running sum and
+// breaks.  FP64 only.  This is the kernel for stores whose weights are not dyadic (the high-interest weight
+// (h_max tan(FOV/2))^2 pi, src/CellFunctions.jl:41-45): there the value of the sum depends on the order of the
+// additions, so it is replayed in list order, one warp per candidate, 32 entries tested at a time and the covered
+// ones added one after the other (every lane forms the same sum).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ordered_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjParams o,
+               const double *__restrict__ X, long long B, EvalOut out, unsigned long long *counter)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5;
+    const uint32_t lane = lane_id();
+    const int N = o.N;
+    const int warp_bytes = round_up(3 * N * 8, 16) + round_up(N * 8, 16);
+    double *stage = reinterpret_cast<double *>(smem_raw + (size_t)warp * warp_bytes);
+    double *Ts = reinterpret_cast<double *>(smem_raw + (size_t)warp * warp_bytes + round_up(3 * N * 8, 16));
+    const int cstride = 3 * N;
+    const double w0 = g.class_weight[0], w1 = g.class_weight[1], w2 = g.class_weight[2], w3 = g.class_weight[3];
+    for (;;) {
+        unsigned long long cand = 0;
+        if (lane == 0) cand = atomicAdd(counter, 1ull);
+        cand = __shfl_sync(0xffffffffu, cand, 0);
+        if ((long long)cand >= B) break;
+        const double *xc = X + (long long)cand * cstride;
+        for (int t = lane; t < cstride; t += 32) stage[t] = xc[t];
+        __syncwarp();
+        for (int c = lane; c < N; c += 32) Ts[c] = threshold(stage[2 * N + c]);
+        const CandScalars cs = candidate_prologue<false>(g, o, stage, nullptr, out.progressive != nullptr);
+        __syncwarp();
+        long long cls_total[kMaxClasses];
+#pragma unroll
+        for (int k = 0; k < kMaxClasses; ++k) cls_total[k] = 0;
+        double area = 0.0;
+        for (long long p0 = 0; p0 < g.n_ent; p0 += 32) {
+            const long long p = p0 + lane;
+            bool cov_entry = false;
+            int k = 0;
+            if (p < g.n_ent) {
+                const int cell = g.ent_cell[p];
+                k = g.ent_cls[p] & (kMaxClasses - 1);
+                const double px = cell_centre(cell % g.nx + 1, g.dx, g.hdx);
+                const double py = cell_centre(cell / g.nx + 1, g.dy, g.hdy);
+                for (int c = 0; c < N; ++c) {
+                    if (radicand(px, py, stage[c], stage[N + c]) < Ts[c]) {
+                        cov_entry = true;
+                        break;
+                    }
+                }
+            }
+            uint32_t m = __ballot_sync(0xffffffffu, cov_entry);
+#pragma unroll
+            for (int q = 0; q < kMaxClasses; ++q)
+                cls_total[q] += __popc(__ballot_sync(0xffffffffu, cov_entry && k == q));
+            while (m) { // list order = ascending lane
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                const int kb = __shfl_sync(0xffffffffu, k, b);
+                area = __dadd_rn(area, kb == 0 ? w0 : (kb == 1 ? w1 : (kb == 2 ? w2 : w3)));
+            }
+        }
+        if (lane == 0) {
+            long long total = 0;
+            for (int k = 0; k < g.n_classes; ++k) total += cls_total[k];
+            out.obj[cand] = __dadd_rn(-area, __dmul_rn(cs.violation, o.penalty_scale));
+            if (out.count) out.count[cand] = total;
+            if (out.feasible) out.feasible[cand] = (unsigned char)cs.feasible;
+            if (out.progressive) out.progressive[cand] = cs.progressive;
+            if (out.class_count)
+                for (int k = 0; k < g.n_classes; ++k) out.class_count[cand * g.n_classes + k] = cls_total[k];
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // launcher
 // ------------------------------------------------------------------------------------------
 template <typename K>
@@ -402,6 +479,23 @@ cudaError_t launch_eval(const GridDesc &g, const ObjParams &o, const LaunchCfg &
     const int N = o.N;
     LaunchInfo li{};
     li.plane_mode = -1;
+    if (cfg.ordered || cfg.kernel == COV_KERNEL_ORDERED) {
+        if (!g.ent_cell && g.n_ent > 0) return cudaErrorInvalidValue; // the caller uploads the list first
+        int warps = 8;
+        while (warps > 1 && warps * (round_up(3 * N * 8, 16) + round_up(N * 8, 16)) > 96 * 1024) warps /= 2;
+        const int smem = warps * (round_up(3 * N * 8, 16) + round_up(N * 8, 16));
+        err = set_smem(ordered_kernel, smem);
+        if (err != cudaSuccess) return err;
+        const long long want = (B + warps - 1) / warps;
+        const int grid = (int)std::min<long long>(want, (long long)cfg.num_sms * 8);
+        ordered_kernel<<<grid, warps * 32, smem, stream>>>(g, o, dX, B, out, counter);
+        li.grid = grid;
+        li.block = warps * 32;
+        li.smem_bytes = smem;
+        li.kernel = COV_KERNEL_ORDERED;
+        if (info) *info = li;
+        return cudaGetLastError();
+    }
     if (cfg.kernel == COV_KERNEL_EXACT) {
         int warps = 8;
         while (warps > 1 && warps * (round_up(3 * N * 8, 16) + round_up(N * 8, 16)) > 96 * 1024) warps /= 2;

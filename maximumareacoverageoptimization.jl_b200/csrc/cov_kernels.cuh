@@ -14,7 +14,8 @@ struct LaunchCfg {
     int force_exact;
     int num_sms;
     int max_smem_optin;  // bytes
-    int plane_mode;      // CTA kernel: -1 auto, 0 lazy global, 1 early global, 2 staged per band (TMA)
+    int plane_mode;      // CTA kernel: -1 auto, 0 lazy global, 1 early global, 2 staged per band (TMA), 3 sweep
+    int ordered;         // 1: the store's area depends on the order of the Float64 additions -> ordered kernel
 };
 
 struct LaunchInfo {

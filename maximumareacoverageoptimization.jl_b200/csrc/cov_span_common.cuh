@@ -122,43 +122,54 @@ static __device__ __noinline__ void slow_span(const GridDesc &g, const double *x
     exact_span(r, lo_e, hi_e, lo, hi);
 }
 
-// Straight-line FP32 estimate + certification of the covered columns of row j for disc d.
+// Straight-line FP32 computation + certification of the covered columns of row j for disc d.
 // Returns kEmpty (certainly no cell), kSpan (certainly exactly [lo, hi]) or kSlow (FP64 decides;
 // lo, hi then hold in-grid guesses for the exact walk).  No branches: two items interleave.
+//
+// Certification without evaluating a single cell.  In the disc's relative frame the cell at column offset u
+// (an integer) has the radicand M(u) = (u dx - fx)^2 + dy2 in real arithmetic on the FP32 inputs; the FP32
+// evaluation s_f32(u) the brute-force kernel uses differs from M(u) by at most 1.5 * 2^-23 s, and s_f32 from the
+// reference's Float64 radicand by at most delta / 2 (delta carries a 2x slack), so with
+// delta2 = 1.25 delta:   M(u) < Tf - delta2  =>  inside,   M(u) > Tf + delta2  =>  outside.
+// Hence cell u is certainly inside when |u dx - fx| < W_in = sqrt(Tf - dy2 - delta2) and certainly outside when
+// |u dx - fx| > W_out = sqrt(Tf - dy2 + delta2).  With W = sqrt(Tf - dy2) and Tf - dy2 >= 8 delta2:
+//     |W_in/out - W| <= 0.52 delta2 / W.
+// The kernel computes w = w2 * rsqrt(w2) (relative error < 2^-20.5 including the rounding of w2) and the two
+// boundary positions xl = (fx - w) / dx, xr = (fx + w) / dx in cell units (relative error < 1.1 * 2^-22 each).
+// Every true boundary position (for W_in and for W_out) therefore lies within
+//     e = 0.75 delta / dx * rsqrt(w2)  +  2^-19.5 * max(|xl|, |xr|)
+// of the computed one (0.75 delta = 0.6 delta2 >= 0.52 delta2 * (1 + 2^-19); 2^-19.5 >= 2^-20.5 + 1.1 * 2^-22
+// with room for the rounding of e itself).  If no integer lies within e of xl nor of xr, then
+// lo = ceil(xl) is certainly inside and lo - 1 certainly outside, hi = floor(xr) likewise, and when
+// ceil(xl) > floor(xr) every column is certainly outside (each integer is left of xl - e or right of xr + e).
+// The differences ceil(xl) - xl and xr - floor(xr) are exact in FP32.  Rows whose chord is too short for the
+// linearisation (Tf - dy2 <= 10 delta) go to the FP64 walk unless the row is certainly outside the disc
+// (dy2 > Tf + 10 delta); so do NaN / Inf / huge / tiny discs (flag bit 0) and every row under force_exact.
 enum { kEmpty = 0, kSpan = 1, kSlow = 2 };
 __device__ __forceinline__ int fast_span(const GridDesc &g, const SDisc &d, int j, int force_exact, int &lo, int &hi)
 {
     const float v = int_to_float_small(j) - d.jcf;
     const float y = fmaf(v, g.dyf, -d.fy);
     const float dy2 = y * y;
-    const float thi = d.Tf + d.delta, tlo = d.Tf - d.delta;
     const float w2 = d.Tf - dy2;
-    // an estimate only (one MUFU, flush-to-zero): whatever it returns, the ends are certified below
+    // one MUFU, flush-to-zero; w2 <= 0 gives Inf / NaN, which `deep` below keeps from being believed
     float rs;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(w2));
-    const float w = w2 > 0.0f ? w2 * rs : 0.0f;
-    const float ulo = ceilf((d.fx - w) * g.inv_dxf);
-    const float uhi = floorf((d.fx + w) * g.inv_dxf);
-    // estimate says "no cell" (a chord shorter than the cell pitch): probe the cell left of the centre
-    // and its right neighbour instead; both certainly outside proves the row empty, because they are
-    // at least as close to the centre as any in-grid cell
-    const bool est_empty = ulo > uhi;
-    const float ua = floorf(d.fx * g.inv_dxf);
+    const float w = w2 * rs;
+    const float xl = (d.fx - w) * g.inv_dxf, xr = (d.fx + w) * g.inv_dxf;
+    const float ulo = ceilf(xl), uhi = floorf(xr);
+    const float e = fmaf(d.delta * g.k_ca, rs, fmaxf(fabsf(xl), fabsf(xr)) * 1.3487e-06f); // 2^-19.5, rounded up
+    const float a = ulo - xl, b = xr - uhi; // distances to the next integer inside the span, in [0, 1)
+    const float w2min = 10.0f * d.delta;
+    const bool deep = w2 > w2min;
+    const bool sure = deep && (fminf(a, b) > e) && (fmaxf(a, b) < 1.0f - e);
     const float nxf = int_to_float_small(g.nx);
-    const float lof = fmaxf(d.icf + (est_empty ? ua : ulo), 1.0f), hif = fminf(d.icf + (est_empty ? ua : uhi), nxf);
-    const float x_lo = fmaf(lof - d.icf, g.dxf, -d.fx), x_hi = fmaf(hif - d.icf, g.dxf, -d.fx);
-    const float x_lm = x_lo - g.dxf, x_hp = x_hi + g.dxf;
-    const float s_lo = fmaf(x_lo, x_lo, dy2), s_hi = fmaf(x_hi, x_hi, dy2);
-    const float s_lm = fmaf(x_lm, x_lm, dy2), s_hp = fmaf(x_hp, x_hp, dy2);
-    const bool ok_span = (s_lo < tlo) && (s_hi < tlo) && (lof == 1.0f || s_lm > thi) && (hif == nxf || s_hp > thi) &&
-                         (lof <= hif);
-    const bool ok_empty = (s_lo > thi) && (s_hp > thi);
+    const float lof = fmaxf(d.icf + ulo, 1.0f), hif = fminf(d.icf + uhi, nxf); // NaN -> the grid edge
     lo = (int)fminf(lof, nxf);
     hi = (int)fmaxf(hif, 1.0f);
+    int st = sure ? ((lof <= hif) ? kSpan : kEmpty) : kSlow;
+    st = (w2 < -w2min) ? kEmpty : st; // the whole row is certainly outside the disc
     const bool irregular = (d.flags & 1u) || force_exact;
-    // branch-free status: irregular -> slow; row certainly outside -> empty; else by the certificates
-    int st = est_empty ? (ok_empty ? kEmpty : kSlow) : (ok_span ? kSpan : kSlow);
-    st = (dy2 > thi) ? kEmpty : st;
     return irregular ? kSlow : st;
 }
 

@@ -389,7 +389,14 @@ cudaError_t launch_span_cta(const GridDesc &g, const ObjParams &o, const LaunchC
     // ahead of the framebuffer atomics for moderate swarms, only when the atomic left new bits for dense ones
     // (measured, B200: staging wins from a few dozen discs per candidate on -- C3 +6 %, C4 +27 % -- and loses
     // for a handful of discs on a big grid, where most of a staged band is never looked at)
-    int mode = multi ? kPlanesLazy : (cfg.plane_mode >= 0 ? cfg.plane_mode : (o.N >= 16 ? kPlanesStaged : kPlanesEarly));
+    // Paint-then-sweep pays a visit to every word of the grid per candidate and saves per painted word: it wins
+    // when the discs cover a good part of the grid or the grid is small (measured, B200: 50 UAVs on 1024^2 +7 %,
+    // 200 on 4096^2 +17 %, 1000 on 4096^2 +44 %, 100 on 2048^2 +7 %, 20 on 256^2 +3 %; 13 on 1024^2 -12 %, 33 on
+    // 512^2 -14 %).  The radii are not known at launch time, so the swarm size decides.
+    const bool sweep_pays = g.planes_q && (o.N >= 40 || (o.N >= 16 && (long long)g.ny * g.qstride <= 4096));
+    int mode = multi ? kPlanesLazy
+                     : (cfg.plane_mode >= 0 ? cfg.plane_mode
+                                            : (sweep_pays ? kPlanesSweep : (o.N >= 16 ? kPlanesStaged : kPlanesEarly)));
     if (multi || (mode == kPlanesSweep && !g.planes_q)) mode = kPlanesLazy;
     CtaPlan p = cta_plan(g, o.N, cfg.max_smem_optin + 1024, cfg.band_rows, cfg.ctas_per_sm,
                          mode == kPlanesStaged || mode == kPlanesSweep, mode == kPlanesSweep);

@@ -141,75 +141,102 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
         __syncwarp();
 
         // ---------------- phase 1: lane k sets up candidate k ----------------
+        // With CHUNK < 32 the other lanes help: lane = cand + CHUNK * part, and the parts share out the discs
+        // (the heavy per-disc record, thresholds included) and the rows of the pair loop; the order-dependent
+        // FP64 sums stay on part 0, the lane that also assembles the candidate in phase 3.
+        constexpr int kParts = 32 / CHUNK;
+        const int cand = (int)lane & (CHUNK - 1), part = (int)lane / CHUNK;
         double my_viol = 0.0, my_prog = 0.0;
         int my_feas = 1;
-        if ((int)lane < in_chunk) {
-            // Rolled loops over the discs (operands re-read through L1): phase 1 runs once per 32
+        {
+            // Rolled loops over the discs (operands re-read from shared memory): phase 1 runs once per CHUNK
             // candidates, so compact code matters more here than a few extra loads.
-            const double *xr = stage + lane * cstride; // shared memory
+            const bool live = cand < in_chunk;
+            const double *xr = stage + (live ? cand : 0) * cstride; // shared memory
             const double *yr = xr + N, *rr = xr + 2 * N;
-            // penalty: sequential FP64 sum in index order (src/TDM_STATIC_opt.jl:89-93)
-#pragma unroll 1
-            for (int i = 0; i < N; ++i) {
-                const double diff = __dsub_rn(rr[i], par[i]);
-                my_viol = __dadd_rn(my_viol, fabs(diff));
-                if (out.progressive && prog_takes(o, i)) my_prog = __dadd_rn(my_prog, julia_max0(diff));
-            }
             bool bad = false;
-            if (o.use_cons3) {
+            if (live && part == 0) {
+                // penalty: sequential FP64 sum in index order (src/TDM_STATIC_opt.jl:89-93)
 #pragma unroll 1
                 for (int i = 0; i < N; ++i) {
-                    const double ax = __dsub_rn(par[N + i], xr[i]);
-                    const double ay = __dsub_rn(par[2 * N + i], yr[i]);
-                    const double az = __dsub_rn(par[3 * N + i], __ddiv_rn(rr[i], o.tan_half_fov));
-                    const double s = __dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az));
-                    bad |= (s >= par[4 * N + i]);
+                    const double diff = __dsub_rn(rr[i], par[i]);
+                    my_viol = __dadd_rn(my_viol, fabs(diff));
+                    if (out.progressive && prog_takes(o, i)) my_prog = __dadd_rn(my_prog, julia_max0(diff));
                 }
-            }
-            if (o.use_cons7) {
+                if (o.use_cons3) {
 #pragma unroll 1
-                for (int i = 0; i < N; ++i) bad |= (yr[i] < 200.0) && (rr[i] > o.cons7_R);
+                    for (int i = 0; i < N; ++i) {
+                        const double ax = __dsub_rn(par[N + i], xr[i]);
+                        const double ay = __dsub_rn(par[2 * N + i], yr[i]);
+                        const double az = __dsub_rn(par[3 * N + i], __ddiv_rn(rr[i], o.tan_half_fov));
+                        const double s = __dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az));
+                        bad |= (s >= par[4 * N + i]);
+                    }
+                }
+                if (o.use_cons7) {
+#pragma unroll 1
+                    for (int i = 0; i < N; ++i) bad |= (yr[i] < 200.0) && (rr[i] > o.cons7_R);
+                }
             }
             // pairs: cons8 (src/TDM_Constraints.jl:157-172; unordered pairs decide the ordered loop) and the
             // discs that may share cells with another disc of the candidate (bounding boxes, two cells of
-            // margin; NaN compares false -> "may share")
+            // margin; NaN compares false -> "may share"); first discs a = part, part + kParts, ...
             uint32_t shared_mask = 0;
+            if (live) {
 #pragma unroll 1
-            for (int a = 0; a < N - 1; ++a) {
-                const double xa = xr[a], ya = yr[a], ra = rr[a];
+                for (int a = part; a < N - 1; a += kParts) {
+                    const double xa = xr[a], ya = yr[a], ra = rr[a];
 #pragma unroll 1
-                for (int b2 = a + 1; b2 < N; ++b2) {
-                    const double ax = __dsub_rn(xa, xr[b2]), ay = __dsub_rn(ya, yr[b2]);
-                    if (o.use_cons8) bad |= (__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)) < o.sep_T);
-                    const double sr = ra + rr[b2];
-                    const bool apart = (fabs(ax) >= sr + 2.0 * g.dx) || (fabs(ay) >= sr + 2.0 * g.dy);
-                    if (!apart) shared_mask |= (1u << a) | (1u << b2);
+                    for (int b2 = a + 1; b2 < N; ++b2) {
+                        const double ax = __dsub_rn(xa, xr[b2]), ay = __dsub_rn(ya, yr[b2]);
+                        if (o.use_cons8) bad |= (__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)) < o.sep_T);
+                        const double sr = ra + rr[b2];
+                        const bool apart = (fabs(ax) >= sr + 2.0 * g.dx) || (fabs(ay) >= sr + 2.0 * g.dy);
+                        if (!apart) shared_mask |= (1u << a) | (1u << b2);
+                    }
+                }
+                // the per-disc records, without the fields that need the whole candidate (patched below)
+#pragma unroll 1
+                for (int c = part; c < N; c += kParts) {
+                    SDisc d;
+                    make_sdisc(g, xr[c], yr[c], rr[c], d);
+                    dp[cand * N + c] = d;
                 }
             }
-            my_feas = !bad;
-            uint32_t run = 0;
-            // 8 x u16 inclusive prefixes; unused slots 0x7fff (above every item index, and small enough for the
-            // packed compare of phase 2)
-            unsigned long long plo = 0x7fff7fff7fff7fffull, phi = 0x7fff7fff7fff7fffull;
-#pragma unroll 1
-            for (int c = 0; c < N; ++c) {
-                SDisc d;
-                const int rows = make_sdisc(g, xr[c], yr[c], rr[c], d);
-                d.flags |= ((shared_mask >> c) & 1u) << 1;
-                // bits 16..31: (first row) - (items before this disc) + 32768, so that item t is row base + t
-                d.flags |= (uint32_t)((int)(d.rows & 0xffffu) - (int)run + 32768) << 16;
-                dp[lane * N + c] = d;
-                run += (uint32_t)rows;
-                const unsigned long long v = run; // ny <= 4095 and N <= 8 keep it below 0x8000
-                const int sh = (c & 3) * 16;
-                if (c < 4) plo = (plo & ~(0xffffull << sh)) | (v << sh);
-                else phi = (phi & ~(0xffffull << sh)) | (v << sh);
+            uint32_t bad_bits = bad ? 1u : 0u;
+#pragma unroll
+            for (int off = CHUNK; off < 32; off <<= 1) { // combine the parts of a candidate
+                shared_mask |= __shfl_xor_sync(0xffffffffu, shared_mask, off);
+                bad_bits |= __shfl_xor_sync(0xffffffffu, bad_bits, off);
             }
-            // slot 7 is never compared against (a disc index needs N - 1 <= 7 prefixes): it carries the total
-            // (N == 8: slot 7 is the last inclusive prefix, which is the total as well); bit 15 of the slot,
-            // free because totals stay below 0x8000: some disc of the candidate goes through the framebuffer
-            phi = (phi & 0x0000ffffffffffffull) | ((unsigned long long)(run | (shared_mask ? 0x8000u : 0u)) << 48);
-            prefix[lane] = make_uint4((uint32_t)plo, (uint32_t)(plo >> 32), (uint32_t)phi, (uint32_t)(phi >> 32));
+            my_feas = !bad_bits;
+            __syncwarp(); // dp[] of the other parts
+            if (live && part == 0) {
+                uint32_t run = 0;
+                // 8 x u16 inclusive prefixes; unused slots 0x7fff (above every item index, and small enough for the
+                // packed compare of phase 2)
+                unsigned long long plo = 0x7fff7fff7fff7fffull, phi = 0x7fff7fff7fff7fffull;
+#pragma unroll 1
+                for (int c = 0; c < N; ++c) {
+                    SDisc *q = dp + cand * N + c;
+                    const uint32_t rws = q->rows;
+                    const int r0 = (int)(rws & 0xffffu), r1 = (int)(rws >> 16);
+                    const int rows = r1 - r0 + 1 > 0 ? r1 - r0 + 1 : 0;
+                    // bit 1: may share cells; bits 16..31: (first row) - (items before this disc) + 32768, so that
+                    // item t is row base + t
+                    q->flags |= (((shared_mask >> c) & 1u) << 1) | ((uint32_t)(r0 - (int)run + 32768) << 16);
+                    run += (uint32_t)rows;
+                    const unsigned long long v = run; // ny <= 4095 and N <= 8 keep it below 0x8000
+                    const int sh = (c & 3) * 16;
+                    if (c < 4) plo = (plo & ~(0xffffull << sh)) | (v << sh);
+                    else phi = (phi & ~(0xffffull << sh)) | (v << sh);
+                }
+                // slot 7 is never compared against (a disc index needs N - 1 <= 7 prefixes): it carries the total
+                // (N == 8: slot 7 is the last inclusive prefix, which is the total as well); bit 15 of the slot,
+                // free because totals stay below 0x8000: some disc of the candidate goes through the framebuffer
+                phi = (phi & 0x0000ffffffffffffull) | ((unsigned long long)(run | (shared_mask ? 0x8000u : 0u)) << 48);
+                prefix[cand] = make_uint4((uint32_t)plo, (uint32_t)(plo >> 32), (uint32_t)phi, (uint32_t)(phi >> 32));
+            }
         }
         __syncwarp();
         // the staging bytes go back to all-zero framebuffer
@@ -296,26 +323,52 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
                         tb += 32;
                     }
                 }
-                // clear what the shared discs painted: every word of their bounding boxes
+                // clear what the shared discs painted
                 if (any_shared) { // warp-uniform
                     __syncwarp();
+                    if (fl.stride <= 16) {
+                        // narrow grids: whole rows from the first to the last row of any shared disc -- one contiguous
+                        // stretch of the framebuffer (the swizzle permutes words within a row only), 128-bit stores
+                        // when rows are 16-byte multiples
+                        int rmin = 0x7fffffff, rmax = 0;
 #pragma unroll 1
-                    for (int c = 0; c < N; ++c) {
-                        const SDisc d = cdp[c];
-                        if (!(d.flags & 2u)) continue;
-                        const int r0 = d.rows & 0xffffu, r1 = d.rows >> 16;
-                        int wa = 0, wb = g.wpr - 1;
-                        if (!(d.flags & 1u)) {
-                            // columns within sqrt(Tf + delta) of the centre, one cell of margin
-                            const float hw = ceilf(sqrtf(d.Tf + d.delta) * g.inv_dxf) + 2.0f;
-                            const float nxf = int_to_float_small(g.nx);
-                            const int ca = (int)fminf(fmaxf(d.icf - hw, 1.0f), nxf);
-                            const int cb = (int)fminf(fmaxf(d.icf + hw, 1.0f), nxf);
-                            wa = (ca - 1) >> 5;
-                            wb = (cb - 1) >> 5;
+                        for (int c = 0; c < N; ++c) {
+                            const uint32_t rows = cdp[c].rows, flg = cdp[c].flags;
+                            const int r0 = rows & 0xffffu, r1 = rows >> 16;
+                            if ((flg & 2u) && r1 >= r0) {
+                                rmin = min(rmin, r0);
+                                rmax = max(rmax, r1);
+                            }
                         }
-                        for (int j = r0 + (int)lane; j <= r1; j += 32) {
-                            for (int w = wa; w <= wb; ++w) fb[fl.at(j - 1, w)] = 0u;
+                        if (rmax >= rmin) {
+                            const int w0 = (rmin - 1) * fl.stride, w1 = rmax * fl.stride; // words [w0, w1)
+                            if ((fl.stride & 3) == 0) {
+                                for (int t = (w0 >> 2) + (int)lane; t < (w1 >> 2); t += 32)
+                                    reinterpret_cast<uint4 *>(fb)[t] = make_uint4(0, 0, 0, 0);
+                            } else {
+                                for (int t = w0 + (int)lane; t < w1; t += 32) fb[t] = 0u;
+                            }
+                        }
+                    } else {
+                        // wide grids: every word of the shared discs' bounding boxes
+#pragma unroll 1
+                        for (int c = 0; c < N; ++c) {
+                            const SDisc d = cdp[c];
+                            if (!(d.flags & 2u)) continue;
+                            const int r0 = d.rows & 0xffffu, r1 = d.rows >> 16;
+                            int wa = 0, wb = g.wpr - 1;
+                            if (!(d.flags & 1u)) {
+                                // columns within sqrt(Tf + delta) of the centre, one cell of margin
+                                const float hw = ceilf(sqrtf(d.Tf + d.delta) * g.inv_dxf) + 2.0f;
+                                const float nxf = int_to_float_small(g.nx);
+                                const int ca = (int)fminf(fmaxf(d.icf - hw, 1.0f), nxf);
+                                const int cb = (int)fminf(fmaxf(d.icf + hw, 1.0f), nxf);
+                                wa = (ca - 1) >> 5;
+                                wb = (cb - 1) >> 5;
+                            }
+                            for (int j = r0 + (int)lane; j <= r1; j += 32) {
+                                for (int w = wa; w <= wb; ++w) fb[fl.at(j - 1, w)] = 0u;
+                            }
                         }
                     }
                 }

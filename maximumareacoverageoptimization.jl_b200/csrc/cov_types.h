@@ -28,6 +28,7 @@ struct GridDesc {
     double inv_dx, inv_dy;
     float dxf, dyf, hdxf, hdyf, inv_dxf, inv_dyf;
     float extent;                    // max(nx*dx, ny*dy): magnitude bound for the FP32 error band
+    float k_ca;                      // 0.75 / dx, rounded up: (band delta) -> (zone half-width * chord), see fast_span
     int plane_class[kMaxPlanes];
     int plane_mult[kMaxPlanes];      // 1, 2, 4, ... entries per set bit
     double class_weight[kMaxClasses];
@@ -38,6 +39,11 @@ struct GridDesc {
     // consecutive rows at one column hit 32 different banks although the rows are aligned.
     int qstride;
     const uint32_t *planes_q;        // device: ny * qstride words (+ padding), or null
+    // The point list in the reference's own order (cell index (i-1) + nx*(j-1) and weight class per entry), for the
+    // ordered kernel; null until a launch needs it.
+    const int *ent_cell;
+    const unsigned char *ent_cls;
+    long long n_ent;
 };
 
 // Captured variables of the reference's closures (createObjective, create_cons3, cons7, cons8).

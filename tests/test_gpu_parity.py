@@ -324,6 +324,77 @@ def test_weight_classes_and_ordered_sum(cov, orc, engine, fire_rows):
         assert obj(X[b]) == orc.objective(X[b], np.full(N, 30 * T), allp)[0]
 
 
+def test_ordered_kernel_non_dyadic_weights_at_scale(cov, orc, engine, fire_rows):
+    """Non-dyadic weights ((h_max tan(FOV/2))^2 pi, src/CellFunctions.jl:41-45): the Float64 area depends on the list
+    order of the additions; the library replays it on the device (ordered kernel).  >= 10^4 candidates through
+    obj.batch, bit for bit against the C restatement; then the list evolves (rmvCoveredPOI, update_POI's push!)."""
+    allp = np.concatenate(fire_rows[:30]).copy()
+    hi = (allp[:, 0] > 200) & (allp[:, 0] < 300) & (allp[:, 1] > 250)
+    allp[hi, 3] = (30.0 * T) ** 2 * math.pi
+    N = 4
+    r_max = np.full(N, 30 * T)
+    ACC = cov.AreaCoverageCalculation
+    pl = ACC.PointList(allp, 100, 100, 5.0, 5.0)
+    res = ACC.ResidentList(pl, engine=engine)
+    obj = cov.TDM_STATIC_opt.createObjective(res, N, r_max)
+    rng = np.random.default_rng(33)
+    X = rand_candidates(rng, 12_000, N)
+    X[:, N:2 * N] = 200 + X[:, N:2 * N] * 0.3
+    got = obj.batch(X)
+    assert engine.grid_info()["area_exact"] == 0 and engine.last_launch()["kernel"] == cov.KERNEL_ORDERED
+    want = orc.eval_batch(X, N, r_max, allp)
+    assert np.array_equal(got.view(np.uint64), want["obj"].view(np.uint64))
+    full = engine.eval_batch(X[:3000], want_class_count=True)
+    assert np.array_equal(full["count"], want["count"][:3000]) and full["class_count"].sum(axis=1).tolist() == want["count"][:3000].tolist()
+    # the order-free formula would differ in the last bits for some candidates (else this test proves nothing)
+    w = engine.class_weights()
+    naive = -(w[0] * full["class_count"][:, 0] + w[1] * full["class_count"][:, 1]) + 1e5 * np.abs(X[:3000, 2 * N:] - r_max).sum(axis=1)
+    assert (naive != want["obj"][:3000]).any()
+    # the list evolves: removal keeps the order of the rest, appended entries go to the end
+    discs = X[int(np.argmax(want["count"]))]
+    ACC.rmvCoveredPOI(discs, res)
+    now = orc.rmvCoveredPOI(discs, allp)
+    assert np.array_equal(res.points.data, now)
+    more = np.concatenate(fire_rows[30:34]).copy()
+    more[::3, 3] = (30.0 * T) ** 2 * math.pi  # (one weight per cell: duplicates within these rows share it below)
+    _, first = np.unique(more[:, :2], axis=0, return_index=True)
+    keyw = {tuple(more[k, :2]): more[k, 3] for k in first}
+    for q in range(len(more)):
+        more[q, 3] = keyw[tuple(more[q, :2])]
+    taken = {tuple(p[:2]): p[3] for p in now}
+    more = more[[tuple(p[:2]) not in taken or taken[tuple(p[:2])] == p[3] for p in more]]
+    res.points.append(more)
+    engine.add_points(more)
+    res.mark_synced()
+    now = np.concatenate([now, more])
+    got2 = obj.batch(X[:4000])
+    want2 = orc.eval_batch(X[:4000], N, r_max, now)
+    assert np.array_equal(got2.view(np.uint64), want2["obj"].view(np.uint64))
+    assert obj(X[5]) == want2["obj"][5] and ACC.calculateArea(X[5], res) == orc.calculateArea(X[5], now)[0]
+
+
+def test_ordered_kernel_as_cross_check(cov, orc, engine, fire_rows):
+    """COV_KERNEL_ORDERED on dyadic stores: the reference's own loop over the list, against the oracle -- on the fire
+    list (duplicates) and on a bit grid, where no list was given and the order is createPOI's."""
+    pts = np.concatenate(fire_rows[:20])
+    engine.set_points(pts, 100, 100, 5.0, 5.0)
+    N = 5
+    r_max = np.full(N, 30 * T)
+    engine.set_params(N, r_max, sep_min=15.0)
+    engine.set_option(cov.OPT_KERNEL, cov.KERNEL_ORDERED)
+    rng = np.random.default_rng(34)
+    X = rand_candidates(rng, 3000, N)
+    X[:, N:2 * N] = 200 + X[:, N:2 * N] * 0.3
+    check_against_oracle(cov, orc, engine, X, N, r_max, pts, sep_min=15.0)
+    assert engine.last_launch()["kernel"] == cov.KERNEL_ORDERED
+    n, d = 256, 500.0 / 256
+    bits, _ = cov.synth.fire_grid(n)
+    engine.set_grid_bits(bits, n, n, d, d)
+    engine.set_params(N, r_max, sep_min=15.0)
+    check_against_oracle(cov, orc, engine, cov.synth.random_candidates(300, N, seed=5), N, r_max,
+                         cov.synth.points_from_bits(bits, n, d, d), sep_min=15.0)
+
+
 def test_remove_covered_and_add_points(cov, orc, engine, fire_rows):
     pts = np.concatenate(fire_rows[:10])
     engine.set_points(pts, 100, 100, 5.0, 5.0)
