@@ -1,4 +1,5 @@
 # Builds libcoverage_cuda.so (sm_100a) and the CPU oracle (test infrastructure).
+EXTRA     ?=
 NVCC      ?= /usr/local/cuda/bin/nvcc
 GCC       ?= /usr/bin/gcc
 PKG       := maximumareacoverageoptimization.jl_b200
@@ -6,7 +7,7 @@ CSRC      := $(PKG)/csrc
 LIB       := $(PKG)/libcoverage_cuda.so
 ORACLE    := oracle/libcoverage_oracle.so
 NVCCFLAGS := --threads 0 -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --fmad=false \
-             -Xcompiler -fPIC,-O2,-fno-fast-math,-ffp-contract=off,-fvisibility=hidden,-pthread -Xptxas -v
+             -Xcompiler -fPIC,-O2,-fno-fast-math,-ffp-contract=off,-fvisibility=hidden,-pthread -Xptxas -v $(EXTRA)
 SRCS      := $(CSRC)/cov_api.cu $(CSRC)/cov_kernels.cu $(CSRC)/cov_span_small.cu $(CSRC)/cov_span_cta.cu $(CSRC)/cov_grid_kernels.cu
 HDRS      := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh) include/coverage_cuda.h
 

@@ -271,6 +271,7 @@ __device__ __forceinline__ void paint_span(const GridDesc &g, uint32_t *fb, cons
                 cnt[0] += __popc(m & pw);
             }
         } else {
+#pragma unroll 1
             for (; w < wb; ++w) { // whole words in between
                 uint32_t m = 0xffffffffu;
                 if (shared) m &= ~atomicOr(fb + fl.at(frow_i, w), m);

@@ -30,8 +30,14 @@
 
 namespace cov {
 
-constexpr int kCtaThreads = 256;
-constexpr int kCtasPerSm = 3;
+#ifndef COV_CTA_THREADS
+#define COV_CTA_THREADS 256 // (overridable for occupancy experiments: make EXTRA="-DCOV_CTA_THREADS=384 -DCOV_CTAS_PER_SM=2")
+#endif
+#ifndef COV_CTAS_PER_SM
+#define COV_CTAS_PER_SM 3
+#endif
+constexpr int kCtaThreads = COV_CTA_THREADS;
+constexpr int kCtasPerSm = COV_CTAS_PER_SM;
 
 struct CtaPlan {
     int fixed_bytes, tab_bytes, fb_bytes, plane_bytes, band_rows, total_bytes, ctas_per_sm;
@@ -110,7 +116,19 @@ __device__ __forceinline__ void paint_only(uint32_t *fb, int qstride, int jb0, i
         --e;
         row[e ^ sw] = 0xffffffffu;
     }
-    for (; s < e; s += 2) *reinterpret_cast<uint2 *>(row + s) = make_uint2(0xffffffffu, 0xffffffffu);
+    // the first eight pairs straight-line and predicated (lanes of a warp have different word counts: a loop would
+    // run for the longest and pay its branches for every lane); whatever is left, in a loop
+    const uint2 ones = make_uint2(0xffffffffu, 0xffffffffu);
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+        if (s + 2 * k < e) *reinterpret_cast<uint2 *>(row + s + 2 * k) = ones;
+    if (__any_sync(__activemask(), s + 4 < e)) { // wide spans only (warp-wide vote: narrow ones skip the block)
+#pragma unroll
+        for (int k = 2; k < 8; ++k)
+            if (s + 2 * k < e) *reinterpret_cast<uint2 *>(row + s + 2 * k) = ones;
+#pragma unroll 1
+        for (s += 16; s < e; s += 2) *reinterpret_cast<uint2 *>(row + s) = ones;
+    }
 }
 
 template <bool MULTI, int PLANES>

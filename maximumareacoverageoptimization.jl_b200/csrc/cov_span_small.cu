@@ -55,7 +55,8 @@ __host__ __device__ inline int small_param_bytes(int N) { return round_up(5 * N 
 
 // MAXW: the most warps a CTA of this instantiation may have (20: <= 102 registers per thread, no spills;
 // 24: <= 85, a few spilled bytes -- worth it when the per-warp shared memory is small enough for 24 warps)
-template <bool MULTI, int CHUNK, int MAXW>
+// FEW: N <= 5 -- the disc index of an item needs 4 prefixes at most, half of the packed compare
+template <bool MULTI, int CHUNK, int MAXW, bool FEW>
 __global__ void __launch_bounds__(MAXW * 32, 1)
 span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjParams o,
                   const double *__restrict__ X, long long B, EvalOut out, unsigned long long *counter,
@@ -97,10 +98,6 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
     fl.stride = fl.swz ? g.wpr : g.stride;
     const long long n_chunks = (B + CHUNK - 1) / CHUNK;
     const int cstride = 3 * N;
-    ItemCtx ictx;
-    ictx.g = &g;
-    ictx.N = N;
-    ictx.force_exact = force_exact;
 
     // units: the first one of a warp is static (warp w of CTA c takes unit c + gridDim.x * w, so a batch of
     // fewer units than warps spreads over all SMs and nobody holds two while another has none); further
@@ -255,7 +252,6 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
             const uint32_t total = (pq.w >> 16) & 0x7fffu; // number of items (slot 7, see phase 1)
             const bool any_shared = (pq.w >> 31) != 0;
             const SDisc *cdp = dp + kc * N;
-            ictx.xrow = X + (base + kc) * cstride;
             uint32_t cnt[MULTI ? kMaxClasses : 1];
 #pragma unroll
             for (int k = 0; k < (MULTI ? kMaxClasses : 1); ++k) cnt[k] = 0;
@@ -279,9 +275,13 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
                         // are below 0x8000) and keeps bit 15 exactly when t >= prefix.  Slot 7 (total | flag) may
                         // borrow out of the top of its word, which harms nothing, and is masked out.
                         const uint32_t rep = tt[k] * 0x10001u + 0x80008000u;
-                        const uint32_t x0 = rep - pq.x, x1 = rep - pq.y, x2 = rep - pq.z, x3 = rep - pq.w;
-                        c[k] = __popc((x0 & 0x80008000u) | ((x1 & 0x80008000u) >> 1) | ((x2 & 0x80008000u) >> 2) |
-                                      ((x3 & 0x00008000u) >> 3));
+                        const uint32_t x0 = rep - pq.x, x1 = rep - pq.y;
+                        uint32_t hits = (x0 & 0x80008000u) | ((x1 & 0x80008000u) >> 1);
+                        if (!FEW) {
+                            const uint32_t x2 = rep - pq.z, x3 = rep - pq.w;
+                            hits |= ((x2 & 0x80008000u) >> 2) | ((x3 & 0x00008000u) >> 3);
+                        }
+                        c[k] = __popc(hits);
                     }
 #pragma unroll
                     for (int k = 0; k < kItems; ++k) {
@@ -299,7 +299,8 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
                     for (int k = 0; k < kItems; ++k)
                         if (st[k] == kSlow) {
                             int l2 = lo[k], h2 = hi[k]; // temporaries: the arrays stay in registers
-                            slow_item(g, ictx.xrow, N, c[k], j[k], (d[k].flags & 1u) || force_exact, l2, h2);
+                            // (the candidate's doubles are only needed here: no address arithmetic per candidate)
+                            slow_item(g, X + (base + kc) * cstride, N, c[k], j[k], (d[k].flags & 1u) || force_exact, l2, h2);
                             if (l2 <= h2) st[k] = kSpan;
                             else { st[k] = kEmpty; l2 = h2 = 1; }
                             lo[k] = l2;
@@ -451,7 +452,7 @@ bool span_small_applies(const GridDesc &g, int N, const LaunchCfg &cfg, long lon
     return true;
 }
 
-template <bool M, int C, int MAXW>
+template <bool M, int C, int MAXW, bool FEW>
 static cudaError_t launch_small_variant(const GridDesc &g, const ObjParams &o, const LaunchCfg &cfg, const double *dX,
                                         long long B, const EvalOut &out, unsigned long long *counter,
                                         cudaStream_t stream, int grid, int warps, int smem)
@@ -461,11 +462,11 @@ static cudaError_t launch_small_variant(const GridDesc &g, const ObjParams &o, c
     int dev = 0;
     (void)cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || smem > configured_smem[dev]) {
-        cudaError_t err = cudaFuncSetAttribute(span_small_kernel<M, C, MAXW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t err = cudaFuncSetAttribute(span_small_kernel<M, C, MAXW, FEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (err != cudaSuccess) return err;
         if (dev >= 0 && dev < 64) configured_smem[dev] = smem;
     }
-    span_small_kernel<M, C, MAXW><<<grid, warps * 32, smem, stream>>>(g, o, dX, B, out, counter, cfg.force_exact);
+    span_small_kernel<M, C, MAXW, FEW><<<grid, warps * 32, smem, stream>>>(g, o, dX, B, out, counter, cfg.force_exact);
     return cudaGetLastError();
 }
 
@@ -493,10 +494,14 @@ cudaError_t launch_span_small(const GridDesc &g, const ObjParams &o, const Launc
         info->max_warps = warps > 20 ? 24 : 20;
         info->plane_mode = -1;
     }
+#define COV_SMALL_ARGS g, o, cfg, dX, B, out, counter, stream, grid, warps, smem
 #define COV_SMALL_CASE(M, C)                                                                                     \
     case C:                                                                                                      \
-        return warps > 20 ? launch_small_variant<M, C, 24>(g, o, cfg, dX, B, out, counter, stream, grid, warps, smem) \
-                          : launch_small_variant<M, C, 20>(g, o, cfg, dX, B, out, counter, stream, grid, warps, smem)
+        if (o.N <= 5)                                                                                            \
+            return warps > 20 ? launch_small_variant<M, C, 24, true>(COV_SMALL_ARGS)                             \
+                              : launch_small_variant<M, C, 20, true>(COV_SMALL_ARGS);                            \
+        return warps > 20 ? launch_small_variant<M, C, 24, false>(COV_SMALL_ARGS)                                \
+                          : launch_small_variant<M, C, 20, false>(COV_SMALL_ARGS)
     if (multi) {
         switch (chunk) {
             COV_SMALL_CASE(true, 32);
@@ -513,6 +518,7 @@ cudaError_t launch_span_small(const GridDesc &g, const ObjParams &o, const Launc
         }
     }
 #undef COV_SMALL_CASE
+#undef COV_SMALL_ARGS
     return cudaErrorInvalidConfiguration;
 }
 
