@@ -270,9 +270,15 @@ __device__ __forceinline__ void paint_span(const GridDesc &g, uint32_t *fb, cons
                 if (shared) m &= ~atomicOr(fb + fl.at(frow_i, w), m);
                 cnt[0] += __popc(m & pw);
             }
+        } else if (WIDE) {
+            for (; w < wb; ++w) { // whole words in between (wide spans: the compiler may unroll)
+                uint32_t m = 0xffffffffu;
+                if (shared) m &= ~atomicOr(fb + fl.at(frow_i, w), m);
+                count_word<MULTI, PLANES_SMEM>(g, prow + w, m, cnt);
+            }
         } else {
 #pragma unroll 1
-            for (; w < wb; ++w) { // whole words in between
+            for (; w < wb; ++w) { // rare in the small-swarm kernel (spans of more than two words): keep the code small
                 uint32_t m = 0xffffffffu;
                 if (shared) m &= ~atomicOr(fb + fl.at(frow_i, w), m);
                 count_word<MULTI, PLANES_SMEM>(g, prow + w, m, cnt);

@@ -10,8 +10,8 @@
 //     lane forms the order-dependent penalty sum;
 //   * the union framebuffer lives in shared memory as a BAND of grid rows (268-row bands at 1024^2 and
 //     96-row bands at 4096^2 when the band's fire words are staged beside it);
-//   * per band the work is cut into units of 32 rows of one disc (a unit -> disc table built by a
-//     CTA-wide scan); warps take units in pairs from a shared-memory dispenser and every lane handles
+//   * per band the work is cut into units of 32 rows of one disc (a unit -> disc table; every thread claims
+//     its discs' slots with one atomicAdd); warps take units in pairs from a shared-memory dispenser and every lane handles
 //     one row of each unit: two independent spans per lane, atomicOr into the band, popcount of the
 //     newly set bits against the fire plane, whose rows for the band are staged in shared memory by ONE
 //     TMA bulk copy per band (cp.async.bulk + mbarrier, issued while the CTA builds the band's unit
@@ -149,12 +149,12 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
     uint32_t *unit_tab = reinterpret_cast<uint32_t *>(scratch + 1024);
     uint32_t *fb = reinterpret_cast<uint32_t *>(scratch + 1024 + cta_tab_bytes(N, band_rows));
     // scratch: [0,8) next candidate; [8,16) violation; [16,24) progressive; [28,32) unit dispenser;
-    //          [32,64) per-warp totals of the unit scan; [512, 512 + nwarps*4*8) per-warp counts
+    //          [32,40) unit counters of even / odd bands; [512, 512 + nwarps*4*8) per-warp counts
     unsigned long long *s_next = reinterpret_cast<unsigned long long *>(scratch);
     double *s_viol = reinterpret_cast<double *>(scratch + 8);
     double *s_prog = reinterpret_cast<double *>(scratch + 16);
     uint32_t *s_disp = reinterpret_cast<uint32_t *>(scratch + 28);
-    uint32_t *s_wtot = reinterpret_cast<uint32_t *>(scratch + 32); // per-warp unit totals of a scan pass
+    uint32_t *s_units = reinterpret_cast<uint32_t *>(scratch + 32); // unit counters of the even / odd bands
     unsigned long long *s_cnt = reinterpret_cast<unsigned long long *>(scratch + 512);
 
     // staged planes: the band's rows of the fire plane, brought in by one TMA bulk copy per band
@@ -195,6 +195,7 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
             d.flags |= 2u; // large swarms overlap as a rule: every disc goes through the framebuffer
             dp[c] = d;
         }
+        if (tid == 0) s_units[0] = s_units[1] = 0;
         if (tid == kCtaThreads - 1) {
             double viol = 0.0, prog = 0.0;
             for (int i = 0; i < N; ++i) {
@@ -239,49 +240,44 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
 #pragma unroll
         for (int k = 0; k < (MULTI ? kMaxClasses : 1); ++k) cls_total[k] = 0;
 
-        // ---- D. bands of framebuffer rows ----
-        for (int jb0 = 1; jb0 <= g.ny; jb0 += band_rows) {
+        // ---- D. bands of framebuffer rows: two CTA barriers per band ----
+        int band = 0;
+        for (int jb0 = 1; jb0 <= g.ny; jb0 += band_rows, ++band) {
             const int jb1 = min(g.ny, jb0 + band_rows - 1);
-            if (kTma && tid == 32) {
+            auto issue_plane_copy = [&]() {
                 // rows jb0..jb1 of the plane are contiguous; (jb0 - 1) * stride is a multiple of 4 words
                 const uint32_t words = (uint32_t)round_up((jb1 - jb0 + 1) * fstride, 4);
                 const uint32_t *src = PLANES == kPlanesSweep ? g.planes_q : g.planes;
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // earlier generic reads of plane_s
                 mbar_expect_tx(bar, words * 4);
                 bulk_g2s(plane_s, src + (size_t)(jb0 - 1) * fstride, words * 4, bar);
-            }
+            };
+            // staged mode reads the plane while painting, and the previous band's painting is over (barrier B)
+            if (PLANES == kPlanesStaged && tid == 32) issue_plane_copy();
             // work units = 32-row blocks of a disc's rows inside the band; unit_tab[u] = (disc, unit within the
-            // disc).  All warps take part: 256 discs per pass, warp-level scans chained through shared memory.
-            if (tid == 0) *s_disp = 0; // the dispenser of this band (its last user finished before the band ended)
-            uint32_t units = 0;        // running total, the same in every thread
+            // disc).  Every thread claims the table slots of its discs with one shared-memory atomicAdd (the
+            // order of the units is immaterial); the counters alternate between bands so that the next band's
+            // counter can be zeroed while this band's is still being read.
+            if (tid == 0) *s_disp = 0; // the dispenser of this band (its last user finished before barrier B)
+            uint32_t *s_u = s_units + (band & 1);
             for (int cb = 0; cb < N; cb += kCtaThreads) {
                 const int c = cb + tid;
-                uint32_t n = 0;
                 if (c < N) {
                     const uint32_t rows = dp[c].rows;
                     const int r0 = max((int)(rows & 0xffffu), jb0), r1 = min((int)(rows >> 16), jb1);
-                    n = r1 >= r0 ? (uint32_t)((r1 - r0 + 32) >> 5) : 0u;
+                    const uint32_t n = r1 >= r0 ? (uint32_t)((r1 - r0 + 32) >> 5) : 0u;
+                    if (n) {
+                        const uint32_t first = atomicAdd(s_u, n);
+                        for (uint32_t k = 0; k < n; ++k) unit_tab[first + k] = ((uint32_t)c << 16) | k;
+                    }
                 }
-                uint32_t incl = n;
-#pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
-                    if (lane >= off) incl += v;
-                }
-                if (lane == 31) s_wtot[warp] = incl;
-                __syncthreads();
-                uint32_t before = 0, all = 0;
-#pragma unroll
-                for (int w = 0; w < nwarps; ++w) {
-                    const uint32_t v = s_wtot[w];
-                    all += v;
-                    before += (w < warp) ? v : 0u;
-                }
-                const uint32_t first = units + before + incl - n; // this disc's units: table entries
-                for (uint32_t k = 0; k < n; ++k) unit_tab[first + k] = ((uint32_t)c << 16) | k;
-                units += all;
-                __syncthreads(); // table entries visible; s_wtot reusable
             }
+            __syncthreads(); // (A) table complete; everybody is done with the previous band (sweep / clear included)
+            const uint32_t units = *s_u;
+            if (tid == 0) s_units[(band + 1) & 1] = 0;
+            // sweep mode needs the plane only after the painting: the copy has the whole paint phase to land, and
+            // issuing it after (A) saves the barrier that would protect the previous band's sweep reads
+            if (PLANES == kPlanesSweep && tid == 32) issue_plane_copy();
             if (PLANES == kPlanesStaged) {
                 mbar_wait(bar, bar_phase);
                 bar_phase ^= 1u;
@@ -291,6 +287,9 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
             if (units != 0) {
                 // warps take units in pairs from the CTA's dispenser: two independent spans per lane
                 for (;;) {
+                    // (dispensing single units towards the end of a band, to shorten the wait at the barrier, was
+                    // measured and lost: a band has only 30-50 units, and two independent spans per lane are worth
+                    // more than a finer tail -- C3 3.22 -> 3.90 ms)
                     uint32_t u0 = 0;
                     if (lane == 0) u0 = atomicAdd(s_disp, 2u);
                     u0 = __shfl_sync(0xffffffffu, u0, 0);
@@ -338,9 +337,9 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
                     }
                 }
             }
-            __syncthreads();
+            __syncthreads(); // (B) the band is painted
             if (PLANES == kPlanesSweep) {
-                mbar_wait(bar, bar_phase); // the band's plane rows (in flight since the band began)
+                mbar_wait(bar, bar_phase); // the band's plane rows (in flight since barrier A)
                 bar_phase ^= 1u;
                 if (units != 0) {
                     // count and clear in one linear pass: framebuffer and plane band have the same layout
@@ -349,13 +348,15 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
                     const uint4 *p4 = reinterpret_cast<const uint4 *>(plane_s);
                     uint32_t c = 0;
                     for (int t = tid; t < (used + 3) / 4; t += kCtaThreads) {
+                        // (skipping unpainted quads -- no plane read, no clear -- was measured: -2 % for 13 UAVs on
+                        // 1024^2, +3 % / +5 % on the C3 / C4 shapes: the branch costs more than it saves)
                         const uint4 f = f4[t], pl = p4[t];
                         c += __popc(f.x & pl.x) + __popc(f.y & pl.y) + __popc(f.z & pl.z) + __popc(f.w & pl.w);
                         f4[t] = make_uint4(0, 0, 0, 0);
                     }
                     cnt[0] += c;
                 }
-                __syncthreads(); // plane_s is overwritten by the next band's copy, issued right away
+                // (no barrier: the next band's table barrier (A) orders this sweep before the next copy and paint)
             } else if (units != 0) {
                 // clear the band for the next band / candidate
                 const int used = (jb1 - jb0 + 1) * g.stride;
@@ -367,8 +368,8 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
                 cls_total[k] += cnt[k];
                 cnt[k] = 0;
             }
-            // the next band's table writes wait for everyone at the __syncthreads above; the clear is ordered
-            // against the next band's painting by the __syncthreads of its unit scan
+            // the next band's table writes wait for everyone at barrier (B); the clear is ordered against the next
+            // band's painting by its barrier (A)
         }
 
         // ---- E. reduce the counts, assemble, write ----
