@@ -1240,3 +1240,38 @@ def test_c4_direct_oracle_sample_1k(cov, orc, engine):
     X = np.concatenate([cov.synth.random_candidates(512, N, seed=13), Xd])
     check_against_oracle(cov, orc, engine, X, N, r_max, pts, sep_min=15.0)
     assert len(X) >= 1000
+
+
+def test_eval_batch_best_and_pipelined_argmin(cov, orc, engine):
+    """cov_eval_batch_best = cov_eval_batch + the poll winner reduced on the device (what one rank contributes to the
+    (min, index) exchange of a sharded poll); cov_argmin takes the sliced pipeline from 4 MiB of candidates on."""
+    engine.set_grid_full(100, 100, 5.0, 5.0)
+    N = 5
+    r_max = np.full(N, 30 * T)
+    rng = np.random.default_rng(78)
+    pre = rand_candidates(rng, 1, N)[0]
+    B = 150_000  # 18 MB of candidates: several 16 MiB-slices of the host pipeline
+    X = pre + rng.normal(0, 3.5, (B, 3 * N))
+    engine.set_params(N, r_max, prev_xyR=pre, d_lim=10.0, tan_half_fov=T)
+    ref = engine.eval_batch(X)
+    feas = ref["feasible"].astype(bool)
+    assert 0 < feas.sum() < B
+    masked = np.where(feas, ref["obj"], np.inf)
+    for barrier in (True, False):
+        r = engine.eval_batch_best(X, barrier=barrier)
+        assert np.array_equal(r["obj"], ref["obj"]) and np.array_equal(r["count"], ref["count"])
+        assert np.array_equal(r["feasible"], ref["feasible"])
+        v = masked if barrier else ref["obj"]
+        assert r["best"] == (v.min(), int(np.argmin(v)))
+        assert engine.argmin(X, barrier=barrier) == r["best"]
+    small = engine.eval_batch_best(X[:30])  # a poll set
+    assert small["best"] == (masked[:30].min(), int(np.argmin(masked[:30]))) or not feas[:30].any()
+    engine.set_params(N, r_max, prev_xyR=pre + 1000.0, d_lim=10.0, tan_half_fov=T)
+    assert engine.eval_batch_best(X)["best"] == (math.inf, -1)
+    # pinned buffers take the same route
+    Xp = engine.pinned((B, 3 * N))
+    Xp[:] = X
+    engine.set_params(N, r_max, prev_xyR=pre, d_lim=10.0, tan_half_fov=T)
+    out = {"obj": engine.pinned((B,)), "count": engine.pinned((B,), np.int64), "feasible": engine.pinned((B,), np.uint8)}
+    r = engine.eval_batch_best(Xp, out=out)
+    assert np.array_equal(out["obj"], ref["obj"]) and r["best"] == (masked.min(), int(np.argmin(masked)))
