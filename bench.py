@@ -89,7 +89,7 @@ def kernel_key(li: dict) -> str:
     if li["kernel"] == 1:
         return f"span_small_kernel<{li['multi']},{li['chunk']},{li['max_warps']}>"
     if li["kernel"] == 4:
-        return f"span_cta_kernel<{li['multi']},{li['plane_mode']}>"
+        return f"span_cta_kernel<{li['multi']},{li['plane_mode']},{li['chunk']}>"
     return {2: "brute_kernel", 3: "exact_kernel"}.get(li["kernel"], f"kernel{li['kernel']}")
 
 

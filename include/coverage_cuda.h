@@ -76,7 +76,9 @@ enum {
     COV_OPT_PLANE_MODE = 9,     /* CTA kernel, how fire words are read: -1 auto (default), 0 through L2 only when
                                    the framebuffer atomic left new bits, 1 through L2 ahead of the atomics,
                                    2 staged in shared memory band by band with TMA bulk copies, 3 paint-then-sweep
-                                   (spans only painted, then popc(framebuffer & staged plane) over the band) */
+                                   (spans only painted, then popc(framebuffer & staged plane) over the band), 4 the
+                                   same with the plane read through L2 in the sweep (no staging: taller bands or a
+                                   fourth CTA per SM; what auto picks unless the swarm is tiny for its grid) */
     COV_OPT_ZEROCOPY_OUT = 8,   /* 1 (default): the host path's kernels write their results straight into pinned host
                                    memory; 0: into device buffers, copied back slice by slice */
     COV_OPT_PROGRESSIVE_INDEX = 10 /* which progressive constraint the `progressive` output of cov_eval_batch_ex is:
@@ -265,7 +267,8 @@ typedef struct cov_launch_info {
     int32_t planes_in_smem; /* 1: bit planes staged in shared memory */
     /* the template instantiation that ran (ABI 2; names the ncu profile bench.py's issue roofline reads) */
     int32_t multi;          /* 1: several bit planes / weight classes / multiplicities */
-    int32_t chunk;          /* small-swarm kernel: candidates per work unit; else 0 */
+    int32_t chunk;          /* small-swarm kernel: candidates per work unit; CTA kernel: co-resident CTAs per SM the
+                               instantiation is compiled for (3 or 4); else 0 */
     int32_t max_warps;      /* small-swarm kernel: warps per CTA the instantiation allows (20 or 24); else 0 */
     int32_t plane_mode;     /* CTA kernel: COV_OPT_PLANE_MODE it resolved to (0, 1, 2); else -1 */
 } cov_launch_info;

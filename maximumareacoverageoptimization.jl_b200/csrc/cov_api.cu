@@ -477,7 +477,7 @@ extern "C" int cov_set_option(cov_handle *h, int option, int64_t value)
         h->zero_copy_out = value != 0;
         return COV_OK;
     case COV_OPT_PLANE_MODE:
-        if (value < -1 || value > 3) return fail(h, COV_ERR_INVALID, "plane mode must be -1..3");
+        if (value < -1 || value > 4) return fail(h, COV_ERR_INVALID, "plane mode must be -1..4");
         h->cfg.plane_mode = (int)value;
         return COV_OK;
     case COV_OPT_PROGRESSIVE_INDEX:

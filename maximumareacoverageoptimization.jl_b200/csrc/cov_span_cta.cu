@@ -50,7 +50,9 @@ struct CtaPlan {
 // cover it, the paint loop has no dependent atomic -> popc chain, and a word painted by k discs costs k cheap
 // stores plus one sweep visit instead of k atomics with return values.  Framebuffer band and staged plane band
 // share the layout of GridDesc::planes_q, so the sweep needs no row / column arithmetic at all.
-enum { kPlanesLazy = 0, kPlanesEarly = 1, kPlanesStaged = 2, kPlanesSweep = 3 };
+// kPlanesSweepL2: the same with the plane read through L2 in the sweep instead of a staged copy -- half the
+// shared memory per CTA, hence more co-resident CTAs or taller bands (an experiment, COV_OPT_PLANE_MODE 4).
+enum { kPlanesLazy = 0, kPlanesEarly = 1, kPlanesStaged = 2, kPlanesSweep = 3, kPlanesSweepL2 = 4 };
 // unit table: one 32-bit entry (disc << 16 | unit within the disc) per 32-row work unit of a band
 __host__ __device__ inline int cta_tab_bytes(int N, int band_rows) { return round_up(N * ((band_rows + 31) / 32) * 4, 16); }
 __host__ __device__ inline int cta_fixed_bytes(int N)
@@ -71,8 +73,9 @@ static CtaPlan cta_plan(const GridDesc &g, int N, int smem_per_sm, int band_rows
         const int budget = smem_per_sm / ctas - 1024; // 1 KB per CTA is reserved by the system
         int rows = (int)((budget - p.fixed_bytes - 4 * N - 16) / (row_bytes + N / 8.0));
         if (rows > g.ny) rows = g.ny;
-        if (staged && rows < g.ny) rows &= ~3; // bands start on 16-byte boundaries of the plane
-        while (rows > 1 && p.fixed_bytes + cta_tab_bytes(N, rows) + round_up(rows * row_bytes, 16) + 32 > budget) rows -= staged ? 4 : 1;
+        const bool aligned = staged || sweep; // bands start on 16-byte boundaries of the plane
+        if (aligned && rows < g.ny) rows &= ~3;
+        while (rows > 1 && p.fixed_bytes + cta_tab_bytes(N, rows) + round_up(rows * row_bytes, 16) + 32 > budget) rows -= aligned ? 4 : 1;
         if (rows >= std::min(g.ny, 80) || ctas == 1) {
             best = ctas;
             p.band_rows = rows;
@@ -80,7 +83,7 @@ static CtaPlan cta_plan(const GridDesc &g, int N, int smem_per_sm, int band_rows
         }
     }
     p.ctas_per_sm = best;
-    if (band_rows_opt > 0 && band_rows_opt < p.band_rows) p.band_rows = staged ? std::max(4, band_rows_opt & ~3) : band_rows_opt;
+    if (band_rows_opt > 0 && band_rows_opt < p.band_rows) p.band_rows = (staged || sweep) ? std::max(4, band_rows_opt & ~3) : band_rows_opt;
     p.fb_bytes = p.band_rows > 0 ? round_up(p.band_rows * fstride * 4, 16) : 0;
     p.plane_bytes = staged && p.band_rows > 0 ? round_up(p.band_rows * fstride * 4, 16) + 16 : 0;
     p.tab_bytes = p.band_rows > 0 ? cta_tab_bytes(N, p.band_rows) : 0;
@@ -131,8 +134,9 @@ __device__ __forceinline__ void paint_only(uint32_t *fb, int qstride, int jb0, i
     }
 }
 
-template <bool MULTI, int PLANES>
-__global__ void __launch_bounds__(kCtaThreads, kCtasPerSm)
+// CTAS: co-resident CTAs per SM the instantiation is compiled for (3: up to 85 registers per thread; 4: 64)
+template <bool MULTI, int PLANES, int CTAS = kCtasPerSm>
+__global__ void __launch_bounds__(kCtaThreads, CTAS)
 span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjParams o,
                 const double *__restrict__ X, long long B, EvalOut out, unsigned long long *counter,
                 int force_exact, int band_rows, int fb_bytes)
@@ -162,7 +166,8 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
     uint64_t *bar = reinterpret_cast<uint64_t *>(plane_s + fb_bytes / 4);
     uint32_t bar_phase = 0;
     constexpr bool kTma = PLANES == kPlanesStaged || PLANES == kPlanesSweep; // the band's plane rows come by TMA
-    const int fstride = PLANES == kPlanesSweep ? g.qstride : g.stride;          // words per framebuffer row
+    constexpr bool kSweep = PLANES == kPlanesSweep || PLANES == kPlanesSweepL2;
+    const int fstride = kSweep ? g.qstride : g.stride;                        // words per framebuffer row
     if (kTma && tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -328,7 +333,7 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
                         lo1 = l2;
                         hi1 = h2;
                     }
-                    if (PLANES == kPlanesSweep) {
+                    if (kSweep) {
                         paint_only(fb, fstride, jb0, jj0, lo0, hi0, st0 == kSpan);
                         paint_only(fb, fstride, jb0, jj1, lo1, hi1, st1 == kSpan);
                     } else {
@@ -338,19 +343,23 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
                 }
             }
             __syncthreads(); // (B) the band is painted
-            if (PLANES == kPlanesSweep) {
-                mbar_wait(bar, bar_phase); // the band's plane rows (in flight since barrier A)
-                bar_phase ^= 1u;
+            if (kSweep) {
+                if (PLANES == kPlanesSweep) {
+                    mbar_wait(bar, bar_phase); // the band's plane rows (in flight since barrier A)
+                    bar_phase ^= 1u;
+                }
                 if (units != 0) {
                     // count and clear in one linear pass: framebuffer and plane band have the same layout
                     const int used = (jb1 - jb0 + 1) * fstride;
                     uint4 *f4 = reinterpret_cast<uint4 *>(fb);
-                    const uint4 *p4 = reinterpret_cast<const uint4 *>(plane_s);
+                    const uint4 *p4 = PLANES == kPlanesSweep
+                                          ? reinterpret_cast<const uint4 *>(plane_s)
+                                          : reinterpret_cast<const uint4 *>(g.planes_q + (size_t)(jb0 - 1) * fstride);
                     uint32_t c = 0;
                     for (int t = tid; t < (used + 3) / 4; t += kCtaThreads) {
                         // (skipping unpainted quads -- no plane read, no clear -- was measured: -2 % for 13 UAVs on
                         // 1024^2, +3 % / +5 % on the C3 / C4 shapes: the branch costs more than it saves)
-                        const uint4 f = f4[t], pl = p4[t];
+                        const uint4 f = f4[t], pl = PLANES == kPlanesSweep ? p4[t] : __ldg(p4 + t);
                         c += __popc(f.x & pl.x) + __popc(f.y & pl.y) + __popc(f.z & pl.z) + __popc(f.w & pl.w);
                         f4[t] = make_uint4(0, 0, 0, 0);
                     }
@@ -408,18 +417,26 @@ cudaError_t launch_span_cta(const GridDesc &g, const ObjParams &o, const LaunchC
     // ahead of the framebuffer atomics for moderate swarms, only when the atomic left new bits for dense ones
     // (measured, B200: staging wins from a few dozen discs per candidate on -- C3 +6 %, C4 +27 % -- and loses
     // for a handful of discs on a big grid, where most of a staged band is never looked at)
-    // Paint-then-sweep pays a visit to every word of the grid per candidate and saves per painted word: it wins
-    // when the discs cover a good part of the grid or the grid is small (measured, B200: 50 UAVs on 1024^2 +7 %,
-    // 200 on 4096^2 +17 %, 1000 on 4096^2 +44 %, 100 on 2048^2 +7 %, 20 on 256^2 +3 %; 13 on 1024^2 -12 %, 33 on
-    // 512^2 -14 %).  The radii are not known at launch time, so the swarm size decides.
-    const bool sweep_pays = g.planes_q && (o.N >= 40 || (o.N >= 16 && (long long)g.ny * g.qstride <= 4096));
+    // Which way to count.  Paint-then-sweep with the plane through L2 (mode 4) is the default: no counting atomics,
+    // no plane band in shared memory, hence a fourth co-resident CTA or taller bands.  Measured on B200 (ms; mode 4
+    // vs the better of early / staged): 50 UAVs on 1024^2 2.95 / 3.45, 200 on 4096^2 5.99 / 8.99, 1000 on 4096^2
+    // 4.93 / 8.48, 100 on 2048^2 2.77 / 3.44, 33 on 512^2 0.84 / 0.94, 20 on 256^2 0.90 / 1.10, 16 on 2048^2
+    // 3.92 / 4.27, 5 on 4096^2 6.56 / 7.87 (many bands: occupancy decides), 5 on 100^2 (1000 candidates) 14 / 18 us.
+    // It loses only where a small swarm leaves most of a grid untouched AND the grid fits two or three bands, so
+    // that the sweep is the larger part of the work: 9 on 1024^2 4.64 / 3.90, 13 on 1024^2 5.00 / 4.68.  The radii
+    // are not known at launch time, so swarm size and grid words decide.
+    const long long grid_words = (long long)g.ny * g.qstride;
+    const bool small_swarm_mid_grid = o.N < 16 && grid_words > 2000ll * o.N && grid_words <= 36000;
     int mode = multi ? kPlanesLazy
                      : (cfg.plane_mode >= 0 ? cfg.plane_mode
-                                            : (sweep_pays ? kPlanesSweep : (o.N >= 16 ? kPlanesStaged : kPlanesEarly)));
-    if (multi || (mode == kPlanesSweep && !g.planes_q)) mode = kPlanesLazy;
-    CtaPlan p = cta_plan(g, o.N, cfg.max_smem_optin + 1024, cfg.band_rows, cfg.ctas_per_sm,
-                         mode == kPlanesStaged || mode == kPlanesSweep, mode == kPlanesSweep);
-    if ((mode == kPlanesStaged || mode == kPlanesSweep) && p.band_rows < 4) {
+                                            : ((g.planes_q && !small_swarm_mid_grid) ? kPlanesSweepL2 : kPlanesEarly));
+    if (multi || ((mode == kPlanesSweep || mode == kPlanesSweepL2) && !g.planes_q)) mode = kPlanesLazy;
+    // the L2 sweep needs no plane band in shared memory: room for a fourth co-resident CTA (its own instantiation,
+    // capped at 64 registers) when the bands stay tall enough
+    const int ctas_try = cfg.ctas_per_sm > 0 ? cfg.ctas_per_sm : (mode == kPlanesSweepL2 ? 4 : kCtasPerSm);
+    CtaPlan p = cta_plan(g, o.N, cfg.max_smem_optin + 1024, cfg.band_rows, ctas_try,
+                         mode == kPlanesStaged || mode == kPlanesSweep, mode == kPlanesSweep || mode == kPlanesSweepL2);
+    if ((mode == kPlanesStaged || mode == kPlanesSweep || mode == kPlanesSweepL2) && p.band_rows < 4) {
         mode = o.N <= 96 ? kPlanesEarly : kPlanesLazy;
         p = cta_plan(g, o.N, cfg.max_smem_optin + 1024, cfg.band_rows, cfg.ctas_per_sm, false);
     }
@@ -433,7 +450,7 @@ cudaError_t launch_span_cta(const GridDesc &g, const ObjParams &o, const LaunchC
         info->planes_in_smem = mode == kPlanesStaged || mode == kPlanesSweep;
         info->kernel = COV_KERNEL_SPAN_GENERAL;
         info->multi = multi;
-        info->chunk = 0;
+        info->chunk = (mode == kPlanesSweepL2 && p.ctas_per_sm >= 4) ? 4 : kCtasPerSm; // CTAs per SM compiled for
         info->max_warps = 0;
         info->plane_mode = mode;
     }
@@ -447,12 +464,24 @@ cudaError_t launch_span_cta(const GridDesc &g, const ObjParams &o, const LaunchC
                                                                             cfg.force_exact, p.band_rows,         \
                                                                             p.fb_bytes);                          \
     } while (0)
+#define COV_LAUNCH_CTA4(M, E)                                                                                     \
+    do {                                                                                                          \
+        err = cudaFuncSetAttribute(span_cta_kernel<M, E, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                   p.total_bytes);                                                                \
+        if (err != cudaSuccess) return err;                                                                       \
+        span_cta_kernel<M, E, 4><<<grid, kCtaThreads, p.total_bytes, stream>>>(g, o, dX, B, out, counter,         \
+                                                                               cfg.force_exact, p.band_rows,      \
+                                                                               p.fb_bytes);                       \
+    } while (0)
     if (multi) COV_LAUNCH_CTA(true, kPlanesLazy);
     else if (mode == kPlanesSweep) COV_LAUNCH_CTA(false, kPlanesSweep);
+    else if (mode == kPlanesSweepL2 && p.ctas_per_sm >= 4) COV_LAUNCH_CTA4(false, kPlanesSweepL2);
+    else if (mode == kPlanesSweepL2) COV_LAUNCH_CTA(false, kPlanesSweepL2);
     else if (mode == kPlanesStaged) COV_LAUNCH_CTA(false, kPlanesStaged);
     else if (mode == kPlanesEarly) COV_LAUNCH_CTA(false, kPlanesEarly);
     else COV_LAUNCH_CTA(false, kPlanesLazy);
 #undef COV_LAUNCH_CTA
+#undef COV_LAUNCH_CTA4
     return cudaGetLastError();
 }
 

@@ -9,8 +9,8 @@ T = cov.TAN_HALF_FOV_DEFAULT
 modes = [int(m) for m in sys.argv[1].split(",")] if len(sys.argv) > 1 else [2, 3]
 e = cov.CoverageEngine(0)
 for n, N, B in ((1024, 50, 65536), (4096, 200, 8192), (1024, 13, 200000), (2048, 100, 16384), (256, 20, 100000),
-                (4096, 1000, 1024), (512, 33, 50000)):
-    bits, nf = cov.synth.fire_grid(n)
+                (4096, 1000, 1024), (512, 33, 50000), (1024, 9, 200000), (4096, 5, 50000), (2048, 16, 50000), (100, 5, 1000)):
+    bits, nf = cov.synth.fire_grid(n, dense=(n == 100))
     d = 500 / n
     e.set_grid_bits(bits, n, n, d, d)
     e.set_params(N, np.full(N, 30 * T), sep_min=15.0)
