@@ -25,6 +25,12 @@ debug-bounds:
 	$(NVCC) $(filter-out -Xptxas -v,$(NVCCFLAGS)) -DCOV_DEBUG_BOUNDS -shared -o build/variants/lib_debug_bounds.so $(SRCS) -cudart static
 	@echo 'run: COVERAGE_CUDA_LIB=$$PWD/build/variants/lib_debug_bounds.so python -m pytest tests -m gpu'
 
+# checking variant: the paint-then-sweep mode paints whole words with atomicOr instead of plain stores
+strict-atomics:
+	mkdir -p build/variants
+	$(NVCC) $(filter-out -Xptxas -v,$(NVCCFLAGS)) -DCOV_STRICT_ATOMICS -shared -o build/variants/lib_strict_atomics.so $(SRCS) -cudart static
+	@echo 'run: COVERAGE_CUDA_LIB=$$PWD/build/variants/lib_strict_atomics.so python -m pytest tests -m gpu'
+
 clean:
 	rm -f $(LIB) $(ORACLE)
-.PHONY: all clean debug-bounds
+.PHONY: all clean debug-bounds strict-atomics

@@ -431,6 +431,8 @@ def e2e_runs(c, eng, cov, wl, B, launches, steps, warmup):
 
     with torch.cuda.stream(c.stream):
         res["pinned_ms"] = timed(call_pinned)
+        if c.world > 1:  # the same call without the winner exchange (what the exchange and its device-side reduction cost)
+            res["noexch_ms"] = timed(lambda k: eng.eval_batch(Xh[k % HOST_SETS], out=out))
         # pageable buffers (plain NumPy arrays: what julia/CoverageCUDA.jl's objective_batch passes)
         Xp = [np.array(x) for x in Xh[:4]]
         outp = {"obj": np.empty(B), "count": np.empty(B, dtype=np.int64), "feasible": np.empty(B, dtype=np.uint8)}
@@ -680,6 +682,10 @@ def main():
             line["e2e_pageable"] = {"value": total / (e["pageable_ms"] * 1e-3), "unit": UNIT,
                                     "ms_per_call": e["pageable_ms"] / calls,
                                     "buffers": "pageable NumPy arrays in and out (what a Julia Vector is)"}
+            if "noexch_ms" in e:
+                line["e2e_no_exchange"] = {"value": total / (e["noexch_ms"] * 1e-3), "unit": UNIT,
+                                           "ms_per_call": e["noexch_ms"] / calls,
+                                           "note": "cov_eval_batch per rank, no exchange between the ranks (every rank for itself)"}
             if "gather_ms" in e:
                 line["e2e_gather"] = {"value": total / (e["gather_ms"] * 1e-3), "unit": UNIT,
                                       "ms_per_call": e["gather_ms"] / calls,

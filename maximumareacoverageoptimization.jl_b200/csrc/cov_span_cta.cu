@@ -111,6 +111,12 @@ __device__ __forceinline__ void paint_only(uint32_t *fb, int qstride, int jb0, i
     atomicOr(row + (wa ^ sw), ma);
     atomicOr(row + (wb ^ sw), mb);
     int s = wa + 1, e = wb; // whole words [s, e)
+#ifdef COV_STRICT_ATOMICS
+    // checking variant (make strict-atomics): whole words by atomicOr as well, so that no plain store ever meets an
+    // atomic on the same word; the GPU suite must give identical results with both builds
+    for (; s < e; ++s) atomicOr(row + (s ^ sw), 0xffffffffu);
+    return;
+#endif
     if (s < e && (s & 1)) {
         row[s ^ sw] = 0xffffffffu;
         ++s;
