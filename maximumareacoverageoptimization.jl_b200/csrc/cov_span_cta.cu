@@ -141,8 +141,10 @@ __device__ __forceinline__ void paint_only(uint32_t *fb, int qstride, int jb0, i
 }
 
 // CTAS: co-resident CTAs per SM the instantiation is compiled for (3: up to 85 registers per thread; 4: 64)
-template <bool MULTI, int PLANES, int CTAS = kCtasPerSm>
-__global__ void __launch_bounds__(kCtaThreads, CTAS)
+// THREADS: 256, or 128 for swarms of up to 64 discs -- twice as many, smaller CTAs per SM: a candidate of a few
+// thousand spans keeps four warps busy as well as eight, and every CTA-wide barrier waits for half as many warps
+template <bool MULTI, int PLANES, int THREADS = kCtaThreads, int CTAS = kCtasPerSm>
+__global__ void __launch_bounds__(THREADS, CTAS)
 span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjParams o,
                 const double *__restrict__ X, long long B, EvalOut out, unsigned long long *counter,
                 int force_exact, int band_rows, int fb_bytes)
@@ -150,7 +152,7 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    constexpr int nwarps = kCtaThreads / 32;
+    constexpr int nwarps = THREADS / 32;
     const int N = o.N;
     const int cstride = 3 * N;
     double *stage = reinterpret_cast<double *>(smem_raw);
@@ -178,7 +180,7 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int t = tid; t < fb_bytes / 16; t += kCtaThreads) reinterpret_cast<uint4 *>(fb)[t] = make_uint4(0, 0, 0, 0);
+    for (int t = tid; t < fb_bytes / 16; t += THREADS) reinterpret_cast<uint4 *>(fb)[t] = make_uint4(0, 0, 0, 0);
 
     // candidates: the first one is the CTA's own index, further ones come from the global dispenser (a poll
     // set, one candidate per CTA, never touches it: two global round trips less on a 10 us kernel)
@@ -195,19 +197,19 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
         const double *xr = X + cand * cstride;
 
         // ---- A. stage the candidate ----
-        for (int t = tid; t < cstride; t += kCtaThreads) stage[t] = __ldg(xr + t);
+        for (int t = tid; t < cstride; t += THREADS) stage[t] = __ldg(xr + t);
         __syncthreads();
 
         // ---- B. disc records (threads from the front) and, at the same time, the order-dependent
         //         penalty sums on the last thread ----
-        for (int c = tid; c < N; c += kCtaThreads) {
+        for (int c = tid; c < N; c += THREADS) {
             SDisc d;
             make_sdisc(g, stage[c], stage[N + c], stage[2 * N + c], d);
             d.flags |= 2u; // large swarms overlap as a rule: every disc goes through the framebuffer
             dp[c] = d;
         }
         if (tid == 0) s_units[0] = s_units[1] = 0;
-        if (tid == kCtaThreads - 1) {
+        if (tid == THREADS - 1) {
             double viol = 0.0, prog = 0.0;
             for (int i = 0; i < N; ++i) {
                 const double diff = __dsub_rn(stage[2 * N + i], o.r_max[i]);
@@ -220,7 +222,7 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
         // ---- C. constraints (everyone; a conjunction, so order-free) ----
         bool bad = false;
         if (o.use_cons3) {
-            for (int i = tid; i < N; i += kCtaThreads) {
+            for (int i = tid; i < N; i += THREADS) {
                 const double ax = __dsub_rn(o.prev_x[i], stage[i]);
                 const double ay = __dsub_rn(o.prev_y[i], stage[N + i]);
                 const double az = __dsub_rn(o.prev_z[i], __ddiv_rn(stage[2 * N + i], o.tan_half_fov));
@@ -229,7 +231,7 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
             }
         }
         if (o.use_cons7) {
-            for (int i = tid; i < N; i += kCtaThreads) bad |= (stage[N + i] < 200.0) && (stage[2 * N + i] > o.cons7_R);
+            for (int i = tid; i < N; i += THREADS) bad |= (stage[N + i] < 200.0) && (stage[2 * N + i] > o.cons7_R);
         }
         if (o.use_cons8) {
             // unordered pairs decide the reference's ordered-pair loop ((xi-xj)^2 is symmetric)
@@ -271,7 +273,7 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
             // counter can be zeroed while this band's is still being read.
             if (tid == 0) *s_disp = 0; // the dispenser of this band (its last user finished before barrier B)
             uint32_t *s_u = s_units + (band & 1);
-            for (int cb = 0; cb < N; cb += kCtaThreads) {
+            for (int cb = 0; cb < N; cb += THREADS) {
                 const int c = cb + tid;
                 if (c < N) {
                     const uint32_t rows = dp[c].rows;
@@ -362,7 +364,7 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
                                           ? reinterpret_cast<const uint4 *>(plane_s)
                                           : reinterpret_cast<const uint4 *>(g.planes_q + (size_t)(jb0 - 1) * fstride);
                     uint32_t c = 0;
-                    for (int t = tid; t < (used + 3) / 4; t += kCtaThreads) {
+                    for (int t = tid; t < (used + 3) / 4; t += THREADS) {
                         // (skipping unpainted quads -- no plane read, no clear -- was measured: -2 % for 13 UAVs on
                         // 1024^2, +3 % / +5 % on the C3 / C4 shapes: the branch costs more than it saves)
                         const uint4 f = f4[t], pl = PLANES == kPlanesSweep ? p4[t] : __ldg(p4 + t);
@@ -375,7 +377,7 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
             } else if (units != 0) {
                 // clear the band for the next band / candidate
                 const int used = (jb1 - jb0 + 1) * g.stride;
-                for (int t = tid; t < (used + 3) / 4; t += kCtaThreads)
+                for (int t = tid; t < (used + 3) / 4; t += THREADS)
                     reinterpret_cast<uint4 *>(fb)[t] = make_uint4(0, 0, 0, 0);
             }
 #pragma unroll
@@ -439,7 +441,15 @@ cudaError_t launch_span_cta(const GridDesc &g, const ObjParams &o, const LaunchC
     if (multi || ((mode == kPlanesSweep || mode == kPlanesSweepL2) && !g.planes_q)) mode = kPlanesLazy;
     // the L2 sweep needs no plane band in shared memory: room for a fourth co-resident CTA (its own instantiation,
     // capped at 64 registers) when the bands stay tall enough
-    const int ctas_try = cfg.ctas_per_sm > 0 ? cfg.ctas_per_sm : (mode == kPlanesSweepL2 ? 4 : kCtasPerSm);
+    // CTA size.  Measured on B200 (ms, 128 threads x 8 CTAs per SM vs 256 x 3 or 4): 9 / 13 UAVs on 1024^2 3.04 / 3.75
+    // vs 3.91 / 4.69, 16 on 2048^2 3.30 vs 3.92, 20 on 256^2 0.65 vs 0.90, 33 on 512^2 0.78 vs 0.84, 50 on 1024^2 2.86
+    // vs 2.95; 100 on 2048^2 2.82 vs 2.77, 200 on 4096^2 7.87 vs 5.98, 1000 on 4096^2 8.71 vs 4.93.
+    const bool small_cta = kCtaThreads == 256 && mode != kPlanesStaged && mode != kPlanesSweep &&
+                           !(mode == kPlanesLazy && !multi) &&
+                           (cfg.warps_per_cta > 0 ? cfg.warps_per_cta <= 4 : o.N <= 64);
+    const int threads = small_cta ? 128 : kCtaThreads;
+    const int ctas_try = cfg.ctas_per_sm > 0 ? cfg.ctas_per_sm
+                                             : (small_cta ? 8 : (mode == kPlanesSweepL2 ? std::max(4, kCtasPerSm) : kCtasPerSm));
     CtaPlan p = cta_plan(g, o.N, cfg.max_smem_optin + 1024, cfg.band_rows, ctas_try,
                          mode == kPlanesStaged || mode == kPlanesSweep, mode == kPlanesSweep || mode == kPlanesSweepL2);
     if ((mode == kPlanesStaged || mode == kPlanesSweep || mode == kPlanesSweepL2) && p.band_rows < 4) {
@@ -450,44 +460,39 @@ cudaError_t launch_span_cta(const GridDesc &g, const ObjParams &o, const LaunchC
     const int grid = (int)std::min<long long>(B, (long long)cfg.num_sms * p.ctas_per_sm);
     if (info) {
         info->grid = grid;
-        info->block = kCtaThreads;
+        info->block = threads;
         info->smem_bytes = p.total_bytes;
         info->band_rows = p.band_rows;
         info->planes_in_smem = mode == kPlanesStaged || mode == kPlanesSweep;
         info->kernel = COV_KERNEL_SPAN_GENERAL;
         info->multi = multi;
-        info->chunk = (mode == kPlanesSweepL2 && p.ctas_per_sm >= 4) ? 4 : kCtasPerSm; // CTAs per SM compiled for
+        info->chunk = small_cta ? 8 : ((mode == kPlanesSweepL2 && p.ctas_per_sm >= 4 && kCtasPerSm < 4) ? 4 : kCtasPerSm); // CTAs per SM compiled for
         info->max_warps = 0;
         info->plane_mode = mode;
     }
     cudaError_t err;
-#define COV_LAUNCH_CTA(M, E)                                                                                      \
+#define COV_LAUNCH_CTA_AS(M, E, T, C)                                                                             \
     do {                                                                                                          \
-        err = cudaFuncSetAttribute(span_cta_kernel<M, E>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+        err = cudaFuncSetAttribute(span_cta_kernel<M, E, T, C>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                                    p.total_bytes);                                                                \
         if (err != cudaSuccess) return err;                                                                       \
-        span_cta_kernel<M, E><<<grid, kCtaThreads, p.total_bytes, stream>>>(g, o, dX, B, out, counter,            \
-                                                                            cfg.force_exact, p.band_rows,         \
-                                                                            p.fb_bytes);                          \
+        span_cta_kernel<M, E, T, C><<<grid, T, p.total_bytes, stream>>>(g, o, dX, B, out, counter,                \
+                                                                        cfg.force_exact, p.band_rows, p.fb_bytes); \
     } while (0)
-#define COV_LAUNCH_CTA4(M, E)                                                                                     \
-    do {                                                                                                          \
-        err = cudaFuncSetAttribute(span_cta_kernel<M, E, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
-                                   p.total_bytes);                                                                \
-        if (err != cudaSuccess) return err;                                                                       \
-        span_cta_kernel<M, E, 4><<<grid, kCtaThreads, p.total_bytes, stream>>>(g, o, dX, B, out, counter,         \
-                                                                               cfg.force_exact, p.band_rows,      \
-                                                                               p.fb_bytes);                       \
-    } while (0)
-    if (multi) COV_LAUNCH_CTA(true, kPlanesLazy);
+#define COV_LAUNCH_CTA(M, E) COV_LAUNCH_CTA_AS(M, E, kCtaThreads, kCtasPerSm)
+    if (small_cta) {
+        if (multi) COV_LAUNCH_CTA_AS(true, kPlanesLazy, 128, 8);
+        else if (mode == kPlanesSweepL2) COV_LAUNCH_CTA_AS(false, kPlanesSweepL2, 128, 8);
+        else COV_LAUNCH_CTA_AS(false, kPlanesEarly, 128, 8);
+    } else if (multi) COV_LAUNCH_CTA(true, kPlanesLazy);
     else if (mode == kPlanesSweep) COV_LAUNCH_CTA(false, kPlanesSweep);
-    else if (mode == kPlanesSweepL2 && p.ctas_per_sm >= 4) COV_LAUNCH_CTA4(false, kPlanesSweepL2);
+    else if (mode == kPlanesSweepL2 && p.ctas_per_sm >= 4 && kCtasPerSm < 4) COV_LAUNCH_CTA_AS(false, kPlanesSweepL2, kCtaThreads, 4);
     else if (mode == kPlanesSweepL2) COV_LAUNCH_CTA(false, kPlanesSweepL2);
     else if (mode == kPlanesStaged) COV_LAUNCH_CTA(false, kPlanesStaged);
     else if (mode == kPlanesEarly) COV_LAUNCH_CTA(false, kPlanesEarly);
     else COV_LAUNCH_CTA(false, kPlanesLazy);
 #undef COV_LAUNCH_CTA
-#undef COV_LAUNCH_CTA4
+#undef COV_LAUNCH_CTA_AS
     return cudaGetLastError();
 }
 
