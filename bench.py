@@ -364,20 +364,23 @@ def device_resident(c, eng, wl, B, launches, steps, warmup, n_sets, seed0, sampl
                 count_sum=int(cnt.sum()), obj_finite=bool(np.isfinite(obj).all()))
 
 
-def h2d_ceiling(c, eng, nbytes=120_000_000, reps=12):
+def h2d_ceiling(c, eng, nbytes=120_000_000, reps=12, sets=4):
     """What the box can do: every rank copies `nbytes` of pinned host memory to its GPU `reps` times, all ranks
-    at once, nothing else running.  GB/s summed over the ranks (max-over-ranks time)."""
+    at once, nothing else running.  The source rotates over `sets` distinct buffers, like the end-to-end run's
+    candidate sets, so that the host's last-level cache cannot stand in for its DRAM.  GB/s summed over the ranks
+    (max-over-ranks time)."""
     torch = c.torch
-    host = eng.pinned((nbytes // 8,))
-    host[:] = 1.0
+    hosts = [eng.pinned((nbytes // 8,)) for _ in range(sets)]
+    for h in hosts:
+        h[:] = 1.0
     dev = eng.device_alloc(nbytes)
     with torch.cuda.stream(c.stream):
-        for _ in range(2):
-            eng.memcpy_h2d(dev, host)
+        for k in range(sets):
+            eng.memcpy_h2d(dev, hosts[k])
         barrier(c)
         t0 = time.perf_counter()
-        for _ in range(reps):
-            eng.memcpy_h2d(dev, host)
+        for k in range(reps):
+            eng.memcpy_h2d(dev, hosts[k % sets])
         c.torch.cuda.synchronize()
         dt = time.perf_counter() - t0
     barrier(c)

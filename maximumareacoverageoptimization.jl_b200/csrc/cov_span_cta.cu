@@ -36,6 +36,14 @@ namespace cov {
 #ifndef COV_CTAS_PER_SM
 #define COV_CTAS_PER_SM 3
 #endif
+#ifndef COV_UNIT_ROWS
+#define COV_UNIT_ROWS 16
+#endif
+// Rows of one disc that form a work unit: 16 -- each half of a warp works on its own unit (its own disc), so that a
+// disc's rows inside a band are rounded up to 16 lanes instead of 32 (32: the whole warp on one unit, round 1's)
+constexpr int kUnitRows = COV_UNIT_ROWS;
+constexpr int kUnitShift = kUnitRows == 8 ? 3 : (kUnitRows == 16 ? 4 : 5);
+static_assert(kUnitRows == 8 || kUnitRows == 16 || kUnitRows == 32, "work units are 8, 16 or 32 rows");
 constexpr int kCtaThreads = COV_CTA_THREADS;
 constexpr int kCtasPerSm = COV_CTAS_PER_SM;
 
@@ -54,7 +62,10 @@ struct CtaPlan {
 // shared memory per CTA, hence more co-resident CTAs or taller bands (an experiment, COV_OPT_PLANE_MODE 4).
 enum { kPlanesLazy = 0, kPlanesEarly = 1, kPlanesStaged = 2, kPlanesSweep = 3, kPlanesSweepL2 = 4 };
 // unit table: one 32-bit entry (disc << 16 | unit within the disc) per 32-row work unit of a band
-__host__ __device__ inline int cta_tab_bytes(int N, int band_rows) { return round_up(N * ((band_rows + 31) / 32) * 4, 16); }
+__host__ __device__ inline int cta_tab_bytes(int N, int band_rows)
+{
+    return round_up(N * ((band_rows + kUnitRows - 1) / kUnitRows) * 4, 16);
+}
 __host__ __device__ inline int cta_fixed_bytes(int N)
 {
     return round_up(3 * N * 8, 16) + N * 32 + round_up((N + 1) * 4, 16) + 1024;
@@ -278,7 +289,7 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
                 if (c < N) {
                     const uint32_t rows = dp[c].rows;
                     const int r0 = max((int)(rows & 0xffffu), jb0), r1 = min((int)(rows >> 16), jb1);
-                    const uint32_t n = r1 >= r0 ? (uint32_t)((r1 - r0 + 32) >> 5) : 0u;
+                    const uint32_t n = r1 >= r0 ? (uint32_t)((r1 - r0 + kUnitRows) >> kUnitShift) : 0u;
                     if (n) {
                         const uint32_t first = atomicAdd(s_u, n);
                         for (uint32_t k = 0; k < n; ++k) unit_tab[first + k] = ((uint32_t)c << 16) | k;
@@ -303,20 +314,25 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
                     // (dispensing single units towards the end of a band, to shorten the wait at the barrier, was
                     // measured and lost: a band has only 30-50 units, and two independent spans per lane are worth
                     // more than a finer tail -- C3 3.22 -> 3.90 ms)
+                    // a warp takes 64 lane-slots of units per iteration: 2 units of 32 rows, or 4 of 16 (lanes 0-15
+                    // and 16-31 then work on different units, hence possibly different discs)
+                    constexpr uint32_t kPerSlot = 32 / kUnitRows; // units side by side in one 32-lane slot
                     uint32_t u0 = 0;
-                    if (lane == 0) u0 = atomicAdd(s_disp, 2u);
+                    if (lane == 0) u0 = atomicAdd(s_disp, 2u * kPerSlot);
                     u0 = __shfl_sync(0xffffffffu, u0, 0);
                     if (u0 >= units) break;
-                    const uint32_t u1 = min(u0 + 1, units - 1);
-                    const bool has1 = u0 + 1 < units;
-                    // disc and position of a unit: one table entry each (warp-uniform broadcast loads)
-                    const uint32_t e0 = unit_tab[u0], e1 = unit_tab[u1];
+                    const uint32_t half = (uint32_t)lane >> kUnitShift; // which unit of the slot this lane works on
+                    const uint32_t ua = u0 + half, ub = u0 + kPerSlot + half;
+                    const bool has0 = ua < units, has1 = ub < units;
+                    // disc and position of a unit: one table entry each (one or two addresses per warp: broadcast)
+                    const uint32_t e0 = unit_tab[min(ua, units - 1)], e1 = unit_tab[min(ub, units - 1)];
                     const int c0 = (int)(e0 >> 16), c1 = (int)(e1 >> 16);
                     COV_ASSERT(c0 >= 0 && c0 < N && c1 >= 0 && c1 < N);
                     const SDisc d0 = dp[c0], d1 = dp[c1];
-                    const int j0 = max((int)(d0.rows & 0xffffu), jb0) + (int)((e0 & 0xffffu) << 5) + lane;
-                    const int j1 = max((int)(d1.rows & 0xffffu), jb0) + (int)((e1 & 0xffffu) << 5) + lane;
-                    const bool in0 = j0 <= min((int)(d0.rows >> 16), jb1);
+                    const int ul = lane & (kUnitRows - 1);
+                    const int j0 = max((int)(d0.rows & 0xffffu), jb0) + (int)((e0 & 0xffffu) << kUnitShift) + ul;
+                    const int j1 = max((int)(d1.rows & 0xffffu), jb0) + (int)((e1 & 0xffffu) << kUnitShift) + ul;
+                    const bool in0 = has0 && j0 <= min((int)(d0.rows >> 16), jb1);
                     const bool in1 = has1 && j1 <= min((int)(d1.rows >> 16), jb1);
                     const int jj0 = in0 ? j0 : jb0, jj1 = in1 ? j1 : jb0; // any row of the band: result discarded
                     COV_ASSERT(jj0 >= jb0 && jj0 <= jb1 && jj1 >= jb0 && jj1 <= jb1);

@@ -33,8 +33,8 @@ def main():
     c.stream = torch.cuda.Stream(device=c.local)
     eng.set_stream(c.stream.cuda_stream)
     out = {}
-    for mb in (16, 120, 480):
-        out[f"{mb}MB"] = bench.h2d_ceiling(c, eng, nbytes=mb * 1_000_000, reps=12)
+    for mb, sets in ((120, 1), (120, 4), (120, 8)):
+        out[f"{mb}MB_x{sets}_buffers"] = bench.h2d_ceiling(c, eng, nbytes=mb * 1_000_000, reps=16, sets=sets)
     if c.rank == 0:
         print(json.dumps({"n_gpus": c.world, "aggregate_h2d_gbs": out, "per_gpu_gbs": {k: v / c.world for k, v in out.items()},
                           "host_placement": note}))
