@@ -3,8 +3,8 @@
 
 Workload (config.workload): BASELINE.json configs[1] -- 5 UAVs x 1 M random candidates per launch on a
 256 x 256 synthetic fire grid, per GPU (weak scaling: every rank evaluates its own candidates).
-One "step" = LAUNCHES (default 32) back-to-back passes of the hot path, each over its own batch of 1 M
-candidates (32 distinct device-resident sets, 3.84 GB), so that 20 steps time > 0.5 s of GPU work.
+One "step" = LAUNCHES (default 40) back-to-back passes of the hot path, each over its own batch of 1 M
+candidates (40 distinct device-resident sets, 4.8 GB), so that 20 steps time > 0.5 s of GPU work.
 
   value      evals/s with the candidates already resident in HBM (cov_eval_batch_device), CUDA events on
              the launching stream, max over ranks.
@@ -50,13 +50,13 @@ sys.path.insert(0, ROOT)
 PKG = os.path.join(ROOT, "maximumareacoverageoptimization.jl_b200")
 
 WORKLOADS = {
-    "c2": dict(n=5, grid=256, batch=1_000_000, sep=0.0, launches=32,
+    "c2": dict(n=5, grid=256, batch=1_000_000, sep=0.0, launches=40,
                name="C2: 5 UAVs x 1M random candidates/launch/GPU, 256x256 synthetic fire grid (BASELINE.json configs[1])"),
     "c3": dict(n=50, grid=1024, batch=65_536, sep=15.0, launches=4,
                name="C3 (reduced batch): 50 UAVs x 64K candidates/launch, 1024x1024 fire grid, cons8 separation (configs[2])"),
     "c4": dict(n=200, grid=4096, batch=8_192, sep=15.0, launches=2,
                name="C4 (reduced batch): 200 UAVs x 8K candidates/launch, 4096x4096 fire grid, cons8 separation (configs[3])"),
-    "c1": dict(n=5, grid=100, batch=1_000_000, sep=0.0, launches=32,
+    "c1": dict(n=5, grid=100, batch=1_000_000, sep=0.0, launches=40,
                name="C1 grid (100x100, dx=5, dense createPOI) with 1M random candidates/launch/GPU"),
 }
 HOST_SETS = 8  # distinct pinned host candidate sets the e2e launches rotate over
