@@ -460,14 +460,21 @@ cudaError_t launch_span_cta(const GridDesc &g, const ObjParams &o, const LaunchC
     // CTA size.  Measured on B200 (ms, 128 threads x 8 CTAs per SM vs 256 x 3 or 4): 9 / 13 UAVs on 1024^2 3.04 / 3.75
     // vs 3.91 / 4.69, 16 on 2048^2 3.30 vs 3.92, 20 on 256^2 0.65 vs 0.90, 33 on 512^2 0.78 vs 0.84, 50 on 1024^2 2.86
     // vs 2.95; 100 on 2048^2 2.82 vs 2.77, 200 on 4096^2 7.87 vs 5.98, 1000 on 4096^2 8.71 vs 4.93.
-    const bool small_cta = kCtaThreads == 256 && mode != kPlanesStaged && mode != kPlanesSweep &&
-                           !(mode == kPlanesLazy && !multi) &&
-                           (cfg.warps_per_cta > 0 ? cfg.warps_per_cta <= 4 : o.N <= 64);
+    bool small_cta = kCtaThreads == 256 && mode != kPlanesStaged && mode != kPlanesSweep &&
+                     !(mode == kPlanesLazy && !multi) && (cfg.warps_per_cta > 0 ? cfg.warps_per_cta <= 4 : o.N <= 64);
+    const bool staged = mode == kPlanesStaged || mode == kPlanesSweep;
+    const bool sweep = mode == kPlanesSweep || mode == kPlanesSweepL2;
+    CtaPlan p{};
+    if (small_cta) {
+        p = cta_plan(g, o.N, cfg.max_smem_optin + 1024, cfg.band_rows, cfg.ctas_per_sm > 0 ? cfg.ctas_per_sm : 8, staged, sweep);
+        // on grids so wide that only a few bands' worth of CTAs fit, 128-thread CTAs would leave the SM short of warps
+        if (cfg.warps_per_cta == 0 && p.ctas_per_sm < 5) small_cta = false;
+    }
     const int threads = small_cta ? 128 : kCtaThreads;
-    const int ctas_try = cfg.ctas_per_sm > 0 ? cfg.ctas_per_sm
-                                             : (small_cta ? 8 : (mode == kPlanesSweepL2 ? std::max(4, kCtasPerSm) : kCtasPerSm));
-    CtaPlan p = cta_plan(g, o.N, cfg.max_smem_optin + 1024, cfg.band_rows, ctas_try,
-                         mode == kPlanesStaged || mode == kPlanesSweep, mode == kPlanesSweep || mode == kPlanesSweepL2);
+    if (!small_cta) {
+        const int ctas_try = cfg.ctas_per_sm > 0 ? cfg.ctas_per_sm : (mode == kPlanesSweepL2 ? std::max(4, kCtasPerSm) : kCtasPerSm);
+        p = cta_plan(g, o.N, cfg.max_smem_optin + 1024, cfg.band_rows, ctas_try, staged, sweep);
+    }
     if ((mode == kPlanesStaged || mode == kPlanesSweep || mode == kPlanesSweepL2) && p.band_rows < 4) {
         mode = o.N <= 96 ? kPlanesEarly : kPlanesLazy;
         p = cta_plan(g, o.N, cfg.max_smem_optin + 1024, cfg.band_rows, cfg.ctas_per_sm, false);
