@@ -2,6 +2,7 @@
 import os
 
 import numpy as np
+import pytest
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -90,3 +91,34 @@ def test_every_python_file_compiles():
     for f in files:
         with open(f) as fh:
             compile(fh.read(), f, "exec")
+
+
+def test_bench_issue_roofline_helpers(tmp_path, monkeypatch):
+    """bench.py's live issue-slot roofline: the kernel key names the template instantiation, a missing capture fails
+    loudly for the named workload, a capture from other sources is flagged stale."""
+    import importlib.util
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    small = {"kernel": 1, "multi": 0, "chunk": 16, "max_warps": 20, "plane_mode": -1}
+    cta = {"kernel": 4, "multi": 0, "chunk": 8, "max_warps": 0, "plane_mode": 4}
+    assert bench.kernel_key(small) == "span_small_kernel<0,16,20>" and bench.kernel_key(cta) == "span_cta_kernel<0,4,8>"
+    prof = {"source_sha": bench.source_sha(), "kernels": {"c2|span_small_kernel<0,16,20>": {
+        "warp_instr_per_candidate": 600.0, "dram_bytes_per_launch": 1.27e8, "issue_active_pct": 74.0}}}
+    v = bench.issue_view(prof, "c2", "span_small_kernel<0,16,20>", 1_000_000, 0.7, 1965.0, strict=True)
+    assert v["bound"] == "issue" and abs(v["achieved"] - 600.0 * 1e6 / 0.7e-3) < 1 and "profile_stale" not in v
+    assert abs(v["peak"] - 148 * 4 * 1965e6) < 1 and abs(v["frac"] - v["achieved"] / v["peak"]) < 1e-12
+    prof["source_sha"] = "0" * 16
+    assert bench.issue_view(prof, "c2", "span_small_kernel<0,16,20>", 1_000_000, 0.7, 1965.0, strict=True)["profile_stale"]
+    monkeypatch.delenv("COV_BENCH_ALLOW_MISSING_PROFILE", raising=False)
+    with pytest.raises(SystemExit):
+        bench.issue_view(prof, "c2", "span_small_kernel<0,4,20>", 1_000_000, 0.7, 1965.0, strict=True)
+    assert bench.issue_view(prof, "c2", "span_small_kernel<0,4,20>", 50_000, 0.1, 1965.0, strict=False)["frac"] is None
+    # the committed capture covers the bench workloads
+    with open(os.path.join(root, "profiles", "r2_issue.json")) as f:
+        committed = json.load(f)
+    assert {k.split("|")[0] for k in committed["kernels"]} >= {"c2", "c3", "c4"}
+    assert len(bench.source_sha()) == 16 and bench.source_sha() == bench.source_sha()
