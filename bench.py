@@ -405,8 +405,9 @@ def e2e_runs(c, eng, cov, wl, B, launches, steps, warmup):
     eng.device_free(tmp)
     out = {"obj": eng.pinned((B,)), "count": eng.pinned((B,), np.int64), "feasible": eng.pinned((B,), np.uint8)}
 
-    pair_dev = torch.zeros(2, dtype=torch.float64, device=f"cuda:{c.local}")
-    pair_all = torch.zeros(2 * c.world, dtype=torch.float64, device=f"cuda:{c.local}")
+    from coverage_b200 import distributed as cdist  # (imports torch.distributed: not part of the package's own imports)
+    scratch = (torch.zeros(2, dtype=torch.float64, device=f"cuda:{c.local}"),
+               torch.zeros(2 * c.world, dtype=torch.float64, device=f"cuda:{c.local}"))
     winners = []
 
     def call_pinned(k):
@@ -416,10 +417,7 @@ def e2e_runs(c, eng, cov, wl, B, launches, steps, warmup):
         # several ranks: the call also yields this rank's poll winner; the ranks exchange the 16-byte pairs
         r = eng.eval_batch_best(Xh[k % HOST_SETS], barrier=True, out=out)
         bo, bi = r["best"]
-        pair_dev.copy_(torch.tensor([bo, float(c.rank * B + bi if bi >= 0 else -1)], dtype=torch.float64))
-        dist.all_gather_into_tensor(pair_all, pair_dev)
-        pa = pair_all.view(c.world, 2).cpu()
-        winners.append(int(torch.argmin(pa[:, 0])))
+        winners.append(cdist.exchange_winner(bo, bi, c.rank * B, scratch)[2])
 
     def timed(fn):
         for k in range(max(warmup, 1) * 2):

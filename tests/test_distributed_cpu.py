@@ -30,7 +30,12 @@ def _worker(rank, world, port, B, q):
     feas = (np.arange(b0, b0 + len(mine)) % 3) != 0
     best = D.argmin_pair(mine, b0, feas)
     none = D.argmin_pair(mine, b0, np.zeros(len(mine), dtype=bool))
-    q.put((rank, full, b0, len(mine), best, none))
+    # every rank already holds its winner (what cov_eval_batch_best returns): the 16-byte exchange
+    v = np.where(feas, mine, np.inf)
+    k = int(np.argmin(v)) if len(v) and np.isfinite(v).any() else -1
+    win = D.exchange_winner(float(v[k]) if k >= 0 else np.inf, k, b0)
+    nobody = D.exchange_winner(np.inf, -1, b0)
+    q.put((rank, full, b0, len(mine), best, none, win, nobody))
     dist.destroy_process_group()
 
 
@@ -63,8 +68,10 @@ def test_gloo_world2_shard_gather_argmin():
     X = rng.random((B, 6))
     want = np.sum((X - 0.3) ** 2, axis=1)
     masked = np.where(np.arange(B) % 3 != 0, want, np.inf)
-    for rank, full, b0, n, best, none in res:
+    for rank, full, b0, n, best, none, win, nobody in res:
         assert np.array_equal(full, want)
         assert (b0, n) == ((0, 501) if rank == 0 else (501, 500))
         assert best == (masked.min(), int(np.argmin(masked)))
         assert none == (np.inf, -1)
+        g = int(np.argmin(masked))
+        assert win == (masked.min(), g, 0 if g < 501 else 1) and nobody == (np.inf, -1, -1)
