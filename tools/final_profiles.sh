@@ -7,5 +7,3 @@ python tools/issue_profile.py run > gpurun_out/issue_plain.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:span_small_kernel -s 1 -c 1 -f -o gpurun_out/r2_final_small_c2 python tools/issue_profile.py run > gpurun_out/ncu_a.log 2>&1; echo rc=$?
 ncu --set full --clock-control none --import-source on -k regex:span_cta_kernel -s 1 -c 1 -f -o gpurun_out/r2_final_cta_c3 python tools/issue_profile.py run > gpurun_out/ncu_b.log 2>&1; echo rc=$?
 ncu --set full --clock-control none --import-source on -k regex:span_cta_kernel -s 4 -c 1 -f -o gpurun_out/r2_final_cta_c4 python tools/issue_profile.py run > gpurun_out/ncu_c.log 2>&1; echo rc=$?
-timeout 300 python tools/full_configs.py c3 --out gpurun_out/r2_full_c3.json 2>&1 | tail -3
-timeout 200 python tools/c1_simulation.py 2>&1 | tail -12
