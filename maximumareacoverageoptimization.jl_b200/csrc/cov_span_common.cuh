@@ -185,6 +185,14 @@ static __device__ __noinline__ void slow_item(const GridDesc &g, const double *x
     slow_span(g, xrow, N, c, j, lo_g, hi_g, lo, hi);
 }
 
+// The same for candidate number `unit_base + k` of the batch: the address of its doubles is formed HERE, inside the
+// out-of-line slow path, so that the callers' hot loops carry no 64-bit address arithmetic for it.
+static __device__ __noinline__ void slow_item_of(const GridDesc &g, const double *X, long long unit_base, int k, int N,
+                                                 int c, int j, bool irregular, int &lo, int &hi)
+{
+    slow_item(g, X + (unit_base + k) * (3ll * N), N, c, j, irregular, lo, hi);
+}
+
 // Count the list entries on columns [lo, hi] of row j.  shared = false: the disc shares no cell with
 // any other disc of the candidate, so its cells are counted directly.  shared = true: the interval
 // is OR-ed into the warp's framebuffer and only the bits this lane was first to set are counted.

@@ -49,7 +49,8 @@ __host__ __device__ inline int small_warp_bytes(const GridDesc &g, int N, int ch
 {
     const int dp = chunk * N * 32;
     const int pre = chunk * 16; // 8 x u16 item prefixes per candidate
-    return small_fb_bytes(g, N, chunk) + dp + pre;
+    const int clr = chunk * 4;  // first | last row << 16 of the discs that go through the framebuffer
+    return small_fb_bytes(g, N, chunk) + dp + pre + clr;
 }
 __host__ __device__ inline int small_param_bytes(int N) { return round_up(5 * N * 8, 16); }
 
@@ -78,6 +79,7 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
     const double *stage = reinterpret_cast<const double *>(wbase);
     SDisc *dp = reinterpret_cast<SDisc *>(wbase + fb_bytes);
     uint4 *prefix = reinterpret_cast<uint4 *>(wbase + fb_bytes + CHUNK * N * 32);
+    uint32_t *clear_rows = reinterpret_cast<uint32_t *>(wbase + fb_bytes + CHUNK * N * 32 + CHUNK * 16);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + planes_bytes + param_bytes + (size_t)warps * warp_bytes);
 
     // the closure parameters once per CTA (with the shared-memory carve-out at its maximum there is next
@@ -210,6 +212,7 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
             __syncwarp(); // dp[] of the other parts
             if (live && part == 0) {
                 uint32_t run = 0;
+                int rmin = 0xffff, rmax = 0; // rows of the discs that paint the framebuffer (what phase 2 clears)
                 // 8 x u16 inclusive prefixes; unused slots 0x7fff (above every item index, and small enough for the
                 // packed compare of phase 2)
                 unsigned long long plo = 0x7fff7fff7fff7fffull, phi = 0x7fff7fff7fff7fffull;
@@ -219,6 +222,10 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
                     const uint32_t rws = q->rows;
                     const int r0 = (int)(rws & 0xffffu), r1 = (int)(rws >> 16);
                     const int rows = r1 - r0 + 1 > 0 ? r1 - r0 + 1 : 0;
+                    if (((shared_mask >> c) & 1u) && rows > 0) {
+                        rmin = min(rmin, r0);
+                        rmax = max(rmax, r1);
+                    }
                     // bit 1: may share cells; bits 16..31: (first row) - (items before this disc) + 32768, so that
                     // item t is row base + t
                     q->flags |= (((shared_mask >> c) & 1u) << 1) | ((uint32_t)(r0 - (int)run + 32768) << 16);
@@ -233,6 +240,7 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
                 // free because totals stay below 0x8000: some disc of the candidate goes through the framebuffer
                 phi = (phi & 0x0000ffffffffffffull) | ((unsigned long long)(run | (shared_mask ? 0x8000u : 0u)) << 48);
                 prefix[cand] = make_uint4((uint32_t)plo, (uint32_t)(plo >> 32), (uint32_t)phi, (uint32_t)(phi >> 32));
+                clear_rows[cand] = (uint32_t)rmin | ((uint32_t)rmax << 16);
             }
         }
         __syncwarp();
@@ -300,7 +308,7 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
                         if (st[k] == kSlow) {
                             int l2 = lo[k], h2 = hi[k]; // temporaries: the arrays stay in registers
                             // (the candidate's doubles are only needed here: no address arithmetic per candidate)
-                            slow_item(g, X + (base + kc) * cstride, N, c[k], j[k], (d[k].flags & 1u) || force_exact, l2, h2);
+                            slow_item_of(g, X, base, kc, N, c[k], j[k], (d[k].flags & 1u) || force_exact, l2, h2);
                             if (l2 <= h2) st[k] = kSpan;
                             else { st[k] = kEmpty; l2 = h2 = 1; }
                             lo[k] = l2;
@@ -331,16 +339,8 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
                         // narrow grids: whole rows from the first to the last row of any shared disc -- one contiguous
                         // stretch of the framebuffer (the swizzle permutes words within a row only), 128-bit stores
                         // when rows are 16-byte multiples
-                        int rmin = 0x7fffffff, rmax = 0;
-#pragma unroll 1
-                        for (int c = 0; c < N; ++c) {
-                            const uint32_t rows = cdp[c].rows, flg = cdp[c].flags;
-                            const int r0 = rows & 0xffffu, r1 = rows >> 16;
-                            if ((flg & 2u) && r1 >= r0) {
-                                rmin = min(rmin, r0);
-                                rmax = max(rmax, r1);
-                            }
-                        }
+                        const uint32_t cr = clear_rows[kc]; // set up in phase 1
+                        const int rmin = (int)(cr & 0xffffu), rmax = (int)(cr >> 16);
                         if (rmax >= rmin) {
                             const int w0 = (rmin - 1) * fl.stride, w1 = rmax * fl.stride; // words [w0, w1)
                             if ((fl.stride & 3) == 0) {
