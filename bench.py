@@ -406,8 +406,7 @@ def e2e_runs(c, eng, cov, wl, B, launches, steps, warmup):
     out = {"obj": eng.pinned((B,)), "count": eng.pinned((B,), np.int64), "feasible": eng.pinned((B,), np.uint8)}
 
     from coverage_b200 import distributed as cdist  # (imports torch.distributed: not part of the package's own imports)
-    scratch = (torch.zeros(2, dtype=torch.float64, device=f"cuda:{c.local}"),
-               torch.zeros(2 * c.world, dtype=torch.float64, device=f"cuda:{c.local}"))
+    scratch = cdist.exchange_scratch() if c.world > 1 else None
     winners = []
 
     def call_pinned(k):

@@ -81,24 +81,37 @@ def argmin_pair(obj_slice: np.ndarray, first: int, feasible: np.ndarray | None =
     return best, idx
 
 
+def exchange_scratch():
+    """Reusable buffers for exchange_winner on the current backend's device: pinned host staging on both sides of
+    the all-gather (two asynchronous 16-byte / 16*world-byte copies and ONE synchronise per exchange)."""
+    world = dist.get_world_size()
+    dev = _device_for_backend()
+    pin = dev.type == "cuda"
+    return {"pair_h": torch.empty(2, dtype=torch.float64, pin_memory=pin),
+            "pair": torch.empty(2, dtype=torch.float64, device=dev),
+            "gathered": torch.empty(2 * world, dtype=torch.float64, device=dev),
+            "gathered_h": torch.empty(2 * world, dtype=torch.float64, pin_memory=pin)}
+
+
 def exchange_winner(best_obj: float, best_idx: int, first: int, scratch=None):
     """The end-of-poll exchange when every rank already holds its own winner (cov_eval_batch_best / cov_argmin reduce
     it on the device): all-gather of one (objective, GLOBAL index) pair per rank -- 16 bytes each -- and the same
     tie rule as argmin_pair (smallest objective, then smallest index).  best_idx < 0: this rank has no feasible
-    candidate.  scratch: optional (pair, gathered) tensors on the backend's device to reuse between calls.
+    candidate.  scratch: exchange_scratch() to reuse between calls.
     Returns (objective, global index, winning rank); (inf, -1, -1) when no rank has a feasible candidate."""
     world = dist.get_world_size()
-    dev = _device_for_backend()
-    if scratch is None:
-        scratch = (torch.empty(2, dtype=torch.float64, device=dev), torch.empty(2 * world, dtype=torch.float64, device=dev))
-    pair, gathered = scratch
-    pair.copy_(torch.tensor([best_obj if best_idx >= 0 else math.inf, float(first + best_idx) if best_idx >= 0 else -1.0],
-                            dtype=torch.float64))
-    if dev.type == "cuda":
-        dist.all_gather_into_tensor(gathered, pair)
+    sc = scratch if scratch is not None else exchange_scratch()
+    sc["pair_h"][0] = best_obj if best_idx >= 0 else math.inf
+    sc["pair_h"][1] = float(first + best_idx) if best_idx >= 0 else -1.0
+    sc["pair"].copy_(sc["pair_h"], non_blocking=True)
+    if sc["pair"].device.type == "cuda":
+        dist.all_gather_into_tensor(sc["gathered"], sc["pair"])
+        sc["gathered_h"].copy_(sc["gathered"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
     else:
-        dist.all_gather(list(gathered.view(world, 2).unbind(0)), pair)
-    rows = gathered.view(world, 2).cpu().tolist()
+        dist.all_gather(list(sc["gathered"].view(world, 2).unbind(0)), sc["pair"])
+        sc["gathered_h"].copy_(sc["gathered"])
+    rows = sc["gathered_h"].view(world, 2).tolist()
     best, idx, who = math.inf, -1, -1
     for r, (o, i) in enumerate(rows):
         if i >= 0 and (idx < 0 or o < best or (o == best and i < idx)):
