@@ -1503,7 +1503,7 @@ static int eval_host(cov_handle *h, const double *X, int64_t B, double *obj, int
             tr(h->stream);
             EvalOut out{};
             const int64_t g0 = w0 + c0;
-            bool zc = h->zero_copy_out != 0 && !best; // the winner is reduced from device-resident results
+            bool zc = h->zero_copy_out != 0 && (obj != nullptr || !best); // (cov_argmin has no per-candidate outputs)
             if (zc) {
                 // results go straight to pinned host memory (the caller's buffer, or the staging block): posted
                 // PCIe writes of 17 B per candidate instead of three D2H copies per slice beside the H2D stream
@@ -1520,6 +1520,10 @@ static int eval_host(cov_handle *h, const double *X, int64_t B, double *obj, int
                     out.feasible = !feasible ? nullptr : (unsigned char *)v_fea + (fea_p ? g0 : c0);
                     out.class_count = !class_count ? nullptr : (long long *)v_cls + (size_t)(cls_p ? g0 : c0) * ncls;
                     out.progressive = !progressive ? nullptr : (double *)v_prg + (prg_p ? g0 : c0);
+                    if (best) { // results straight to the host as usual; the winner is reduced from device mirrors
+                        out.obj_mirror = (double *)h->d_obj.p + c0;
+                        out.feasible_mirror = (unsigned char *)h->d_feas.p + c0;
+                    }
                 }
             }
             if (!zc) {

@@ -26,6 +26,15 @@ __device__ __forceinline__ bool prog_takes(const ObjParams &o, int i) { return o
 
 __host__ __device__ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+// The mirrors of EvalOut (device copies of objective and feasibility for the winner reduction).
+__device__ __forceinline__ void store_mirrors(const EvalOut &out, long long idx, double obj, int feasible)
+{
+    if (out.obj_mirror) {
+        out.obj_mirror[idx] = obj;
+        out.feasible_mirror[idx] = (unsigned char)feasible;
+    }
+}
+
 // obj = -area + violation*scale, area from exact integer counts (see cov_grid_info.area_exact)
 __device__ __forceinline__ double assemble_objective(const GridDesc &g, const ObjParams &o,
                                                      const long long *class_cnt, double violation)

@@ -307,6 +307,7 @@ brute_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjPara
         if ((int)lane < in_chunk) {
             const long long bidx = base + lane;
             out.obj[bidx] = my_obj;
+            store_mirrors(out, bidx, my_obj, my_feas);
             if (out.count) out.count[bidx] = my_cnt;
             if (out.feasible) out.feasible[bidx] = (unsigned char)my_feas;
             if (out.progressive) out.progressive[bidx] = my_prog;
@@ -373,7 +374,9 @@ exact_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjPara
         if (lane == 0) {
             long long total = 0;
             for (int k = 0; k < g.n_classes; ++k) total += cls_total[k];
-            out.obj[cand] = assemble_objective(g, o, cls_total, cs.violation);
+            const double my_obj = assemble_objective(g, o, cls_total, cs.violation);
+            out.obj[cand] = my_obj;
+            store_mirrors(out, cand, my_obj, cs.feasible);
             if (out.count) out.count[cand] = total;
             if (out.feasible) out.feasible[cand] = (unsigned char)cs.feasible;
             if (out.progressive) out.progressive[cand] = cs.progressive;
@@ -450,7 +453,9 @@ ordered_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjPa
         if (lane == 0) {
             long long total = 0;
             for (int k = 0; k < g.n_classes; ++k) total += cls_total[k];
-            out.obj[cand] = __dadd_rn(-area, __dmul_rn(cs.violation, o.penalty_scale));
+            const double my_obj = __dadd_rn(-area, __dmul_rn(cs.violation, o.penalty_scale));
+            out.obj[cand] = my_obj;
+            store_mirrors(out, cand, my_obj, cs.feasible);
             if (out.count) out.count[cand] = total;
             if (out.feasible) out.feasible[cand] = (unsigned char)cs.feasible;
             if (out.progressive) out.progressive[cand] = cs.progressive;

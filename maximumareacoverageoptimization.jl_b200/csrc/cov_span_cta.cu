@@ -422,7 +422,9 @@ span_cta_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ ObjP
                     for (int w = 0; w < nwarps; ++w) tot[k] += (long long)s_cnt[w * kMaxClasses + k];
                 total_cnt += tot[k];
             }
-            out.obj[cand] = assemble_objective(g, o, tot, *s_viol);
+            const double my_obj = assemble_objective(g, o, tot, *s_viol);
+            out.obj[cand] = my_obj;
+            store_mirrors(out, cand, my_obj, any_bad ? 0 : 1);
             if (out.count) out.count[cand] = total_cnt;
             if (out.feasible) out.feasible[cand] = (unsigned char)(any_bad ? 0 : 1);
             if (out.progressive) out.progressive[cand] = *s_prog;

@@ -389,7 +389,9 @@ span_small_kernel(const __grid_constant__ GridDesc g, const __grid_constant__ Ob
         // ---------------- phase 3: lane k finishes candidate k; coalesced stores ----------------
         if ((int)lane < in_chunk) {
             const long long bidx = base + lane;
-            out.obj[bidx] = assemble_objective(g, o, my_cls, my_viol);
+            const double my_obj = assemble_objective(g, o, my_cls, my_viol);
+            out.obj[bidx] = my_obj;
+            store_mirrors(out, bidx, my_obj, my_feas);
             if (out.count) out.count[bidx] = my_cnt;
             if (out.feasible) out.feasible[bidx] = (unsigned char)my_feas;
             if (out.progressive) out.progressive[bidx] = my_prog;

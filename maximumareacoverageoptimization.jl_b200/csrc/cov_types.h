@@ -69,6 +69,10 @@ struct EvalOut {
     unsigned char *feasible; // B or null
     long long *class_count; // B * n_classes or null
     double *progressive;    // B or null
+    // device-resident mirrors of obj / feasible (both or neither; null as a rule): what the winner reduction of
+    // cov_eval_batch_best reads when the results themselves go straight to pinned host memory
+    double *obj_mirror;
+    unsigned char *feasible_mirror;
 };
 
 } // namespace cov
