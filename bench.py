@@ -364,23 +364,36 @@ def device_resident(c, eng, wl, B, launches, steps, warmup, n_sets, seed0, sampl
                 count_sum=int(cnt.sum()), obj_finite=bool(np.isfinite(obj).all()))
 
 
-def h2d_ceiling(c, eng, nbytes=120_000_000, reps=12, sets=4):
+def h2d_ceiling(c, eng, nbytes=120_000_000, reps=12, sets=4, d2h_bytes=0):
     """What the box can do: every rank copies `nbytes` of pinned host memory to its GPU `reps` times, all ranks
     at once, nothing else running.  The source rotates over `sets` distinct buffers, like the end-to-end run's
     candidate sets, so that the host's last-level cache cannot stand in for its DRAM.  GB/s summed over the ranks
-    (max-over-ranks time)."""
+    (max-over-ranks time).
+    d2h_bytes > 0: the same with the path's result traffic flowing the other way -- beside copy k+1 a second stream
+    copies d2h_bytes (17 B per candidate of copy k) from the device into pinned host memory.  Still H2D GB/s."""
     torch = c.torch
     hosts = [eng.pinned((nbytes // 8,)) for _ in range(sets)]
     for h in hosts:
         h[:] = 1.0
     dev = eng.device_alloc(nbytes)
+    back = None
+    if d2h_bytes:
+        back = (torch.zeros(d2h_bytes, dtype=torch.uint8, device=torch.device("cuda", c.local)),
+                torch.empty(d2h_bytes, dtype=torch.uint8, pin_memory=True), torch.cuda.Stream(device=c.local))
     with torch.cuda.stream(c.stream):
         for k in range(sets):
             eng.memcpy_h2d(dev, hosts[k])
+        c.torch.cuda.synchronize()
         barrier(c)
         t0 = time.perf_counter()
         for k in range(reps):
             eng.memcpy_h2d(dev, hosts[k % sets])
+            if back is not None:
+                ev = torch.cuda.Event()
+                ev.record(c.stream)
+                back[2].wait_event(ev)
+                with torch.cuda.stream(back[2]):
+                    back[1].copy_(back[0], non_blocking=True)
         c.torch.cuda.synchronize()
         dt = time.perf_counter() - t0
     barrier(c)
@@ -631,6 +644,7 @@ def main():
     ceiling = None
     if not args.no_e2e:
         ceiling = h2d_ceiling(c, eng, nbytes=B * row_bytes)
+        ceiling_duplex = h2d_ceiling(c, eng, nbytes=B * row_bytes, d2h_bytes=B * 17)
         e = e2e_runs(c, eng, cov, wl, B, L, args.steps, args.warmup)
 
     profile = load_issue_profile()
@@ -694,6 +708,9 @@ def main():
                                       "h2d_bytes_per_step": B * row_bytes * L, "d2h_bytes_per_step": B * 8 * c.world * L}
             line["h2d_ceiling_gbs"] = ceiling
             line["e2e_frac_of_h2d_ceiling"] = e2e * row_bytes / 1e9 / ceiling
+            # the same copies with the results' 17 B per candidate going back at the same time (what the path moves)
+            line["h2d_ceiling_with_results_gbs"] = ceiling_duplex
+            line["e2e_frac_of_ceiling_with_results"] = e2e * row_bytes / 1e9 / ceiling_duplex
     if not args.no_extra and args.workload == "c2":
         extras = [extra_workload(c, cov, synth, name, profile, sm_mhz) for name in ("c3", "c4")]
         if c.rank == 0:

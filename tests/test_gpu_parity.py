@@ -970,8 +970,9 @@ def test_bench_line_contract(cov):
     d = json.loads(lines[0])
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "roofline", "roofline_hbm", "cpu_baseline", "e2e", "e2e_pageable",
-              "gpu_launches", "clocks", "extra_workloads", "h2d_ceiling_gbs"):
+              "gpu_launches", "clocks", "extra_workloads", "h2d_ceiling_gbs", "h2d_ceiling_with_results_gbs"):
         assert k in d, k
+    assert 0 < d["h2d_ceiling_with_results_gbs"] <= d["h2d_ceiling_gbs"] * 1.1
     assert d["n_gpus"] == 1 and d["steps"] == 2 and d["value"] > 0 and d["gpu_launches"] == 2 * 3
     # the bound that matters is instruction issue; a non-default batch may run an instantiation without a capture
     assert d["roofline"]["bound"] == "issue" and d["roofline"]["kernel"].startswith("span_small_kernel<")

@@ -35,6 +35,8 @@ def main():
     out = {}
     for mb, sets in ((120, 1), (120, 4), (120, 8)):
         out[f"{mb}MB_x{sets}_buffers"] = bench.h2d_ceiling(c, eng, nbytes=mb * 1_000_000, reps=16, sets=sets)
+    # ... and with the path's result traffic (17 B per candidate = 17 MB per 120 MB copy) flowing back at the same time
+    out["120MB_x4_buffers_with_17MB_d2h"] = bench.h2d_ceiling(c, eng, nbytes=120_000_000, reps=16, sets=4, d2h_bytes=17_000_000)
     if c.rank == 0:
         print(json.dumps({"n_gpus": c.world, "aggregate_h2d_gbs": out, "per_gpu_gbs": {k: v / c.world for k, v in out.items()},
                           "host_placement": note}))
