@@ -70,8 +70,22 @@ __host__ __device__ inline int cta_fixed_bytes(int N)
 {
     return round_up(3 * N * 8, 16) + N * 32 + round_up((N + 1) * 4, 16) + 1024;
 }
+// A band must hold at least this many rows before another co-resident CTA is worth its shared memory.  Measured on
+// B200 (tools/band_threshold_exp.py; ms at 80 / 56 / 48 / 40): 5 UAVs on 4096^2 6.13 / 5.72 / 5.52 / 5.52, 20 on
+// 4096^2 7.78 / 7.54 / 7.22 / 7.22, 1000 on 4096^2 4.97 / 3.62 / 3.62 / 3.62 (two CTAs instead of one), 50 on 8192^2
+// 12.20 / 11.53 / 10.62 / 10.63, 200 on 8192^2 7.76 / 7.10 / 7.11 / 7.10; 200 on 4096^2 (C4) does not care whether it
+// runs three CTAs with 108-row bands or four with 76 (5.86 / 5.87 / 5.86 / 5.85), nor 400 on 4096^2 (3 x 80 rows 3.91,
+// 4 x 48 rows 3.87-3.90) -- but four CTAs execute 8 % more instructions for it (more bands: more tables, barriers and
+// sweep set-up), so for swarms of 128 discs and more a FOURTH 256-thread CTA still has to leave 80-row bands (the
+// per-band tables grow with the swarm; 50 UAVs on 8192^2 do gain from the fourth CTA: 3 x 68 rows 11.53, 4 x 48 10.62).
+#ifndef COV_MIN_BAND_ROWS
+#define COV_MIN_BAND_ROWS 48
+#endif
+#ifndef COV_MIN_BAND_ROWS_4TH
+#define COV_MIN_BAND_ROWS_4TH 80
+#endif
 static CtaPlan cta_plan(const GridDesc &g, int N, int smem_per_sm, int band_rows_opt, int ctas_opt, bool staged,
-                        bool sweep = false)
+                        bool sweep = false, int threads = kCtaThreads)
 {
     CtaPlan p{};
     p.fixed_bytes = cta_fixed_bytes(N) + (staged ? 32 : 0); // + the band's plane rows and an mbarrier when staged
@@ -87,7 +101,8 @@ static CtaPlan cta_plan(const GridDesc &g, int N, int smem_per_sm, int band_rows
         const bool aligned = staged || sweep; // bands start on 16-byte boundaries of the plane
         if (aligned && rows < g.ny) rows &= ~3;
         while (rows > 1 && p.fixed_bytes + cta_tab_bytes(N, rows) + round_up(rows * row_bytes, 16) + 32 > budget) rows -= aligned ? 4 : 1;
-        if (rows >= std::min(g.ny, 80) || ctas == 1) {
+        const int need = (threads >= 256 && ctas >= 4 && N >= 128) ? COV_MIN_BAND_ROWS_4TH : COV_MIN_BAND_ROWS;
+        if (rows >= std::min(g.ny, need) || ctas == 1) {
             best = ctas;
             p.band_rows = rows;
             break;
@@ -467,16 +482,19 @@ cudaError_t launch_span_cta(const GridDesc &g, const ObjParams &o, const LaunchC
     const bool staged = mode == kPlanesStaged || mode == kPlanesSweep;
     const bool sweep = mode == kPlanesSweep || mode == kPlanesSweepL2;
     CtaPlan p{};
+    const int big_ctas_try = cfg.ctas_per_sm > 0 ? cfg.ctas_per_sm : (mode == kPlanesSweepL2 ? std::max(4, kCtasPerSm) : kCtasPerSm);
     if (small_cta) {
-        p = cta_plan(g, o.N, cfg.max_smem_optin + 1024, cfg.band_rows, cfg.ctas_per_sm > 0 ? cfg.ctas_per_sm : 8, staged, sweep);
-        // on grids so wide that only a few bands' worth of CTAs fit, 128-thread CTAs would leave the SM short of warps
-        if (cfg.warps_per_cta == 0 && p.ctas_per_sm < 5) small_cta = false;
+        p = cta_plan(g, o.N, cfg.max_smem_optin + 1024, cfg.band_rows, cfg.ctas_per_sm > 0 ? cfg.ctas_per_sm : 8, staged, sweep, 128);
+        // on grids so wide that only a few bands' worth of CTAs fit, 128-thread CTAs would leave the SM short of warps:
+        // they must bring at least as many warps per SM as the 256-thread plan (50 UAVs on 4096^2: 7 x 128 threads
+        // 7.17 ms, 4 x 256 7.04 ms)
+        if (cfg.warps_per_cta == 0) {
+            const CtaPlan big = cta_plan(g, o.N, cfg.max_smem_optin + 1024, cfg.band_rows, big_ctas_try, staged, sweep);
+            if (p.ctas_per_sm < 5 || p.ctas_per_sm * 4 < big.ctas_per_sm * 8) small_cta = false;
+        }
     }
     const int threads = small_cta ? 128 : kCtaThreads;
-    if (!small_cta) {
-        const int ctas_try = cfg.ctas_per_sm > 0 ? cfg.ctas_per_sm : (mode == kPlanesSweepL2 ? std::max(4, kCtasPerSm) : kCtasPerSm);
-        p = cta_plan(g, o.N, cfg.max_smem_optin + 1024, cfg.band_rows, ctas_try, staged, sweep);
-    }
+    if (!small_cta) p = cta_plan(g, o.N, cfg.max_smem_optin + 1024, cfg.band_rows, big_ctas_try, staged, sweep);
     if ((mode == kPlanesStaged || mode == kPlanesSweep || mode == kPlanesSweepL2) && p.band_rows < 4) {
         mode = o.N <= 96 ? kPlanesEarly : kPlanesLazy;
         p = cta_plan(g, o.N, cfg.max_smem_optin + 1024, cfg.band_rows, cfg.ctas_per_sm, false);
