@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define COV_ABI_VERSION 2 /* 2: COV_OPT_PROGRESSIVE_INDEX, cov_get_class_weights, cov_eval_area_ordered */
+#define COV_ABI_VERSION 2 /* 2: COV_OPT_PROGRESSIVE_INDEX, COV_KERNEL_ORDERED, cov_get_class_weights, cov_eval_batch_best */
 
 #if defined(__GNUC__)
 #define COV_API __attribute__((visibility("default")))

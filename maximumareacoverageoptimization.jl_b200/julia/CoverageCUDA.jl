@@ -161,6 +161,29 @@ function objective_batch!(h::Handle, b::BatchBuffers, n::Integer = size(b.X, 2))
 end
 
 """
+    objective_batch_best!(h, bufs, n; barrier = true) -> (obj, count, feasible, best_obj, best_column)
+
+`objective_batch!` plus the poll winner reduced on the device (`cov_eval_batch_best`): the 16 bytes a process
+contributes when the candidates of one poll are sharded over several GPUs (one Julia process per GPU, e.g. under
+MPI.jl or Distributed: `MPI.Allgather((best_obj, first_column + best_column))`, smallest objective wins, ties to the
+smallest column). `best_column` is 1-based, 0 when no candidate is feasible.
+"""
+function objective_batch_best!(h::Handle, b::BatchBuffers, n::Integer = size(b.X, 2); barrier = true)
+    bo = Ref{Float64}(Inf); bi = Ref{Int64}(-1)
+    check(h, ccall((:cov_eval_batch_best, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Int64}, Ptr{UInt8}, Int32, Ref{Float64}, Ref{Int64}),
+        h.ptr, b.X, n, b.obj, b.count, b.feasible, barrier ? 1 : 0, bo, bi))
+    return view(b.obj, 1:n), view(b.count, 1:n), view(b.feasible, 1:n), bo[], bi[] + 1
+end
+
+"The store's weight classes in the device's numbering (the `class_count` columns of `cov_eval_batch_ex`)."
+function class_weights(h::Handle)
+    w = zeros(Float64, 4)
+    check(h, ccall((:cov_get_class_weights, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), h.ptr, w, 4))
+    return w
+end
+
+"""
     create_cons1_progressive(N, r_max) / create_cons2_progressive / create_cons3_progressive
 
 The progressive constraints of src/TDM_Constraints.jl:182-221 (`x -> Real`, for `AddProgressiveConstraint`):
