@@ -451,6 +451,29 @@ def e2e_runs(c, eng, cov, wl, B, launches, steps, warmup):
         outp = {"obj": np.empty(B), "count": np.empty(B, dtype=np.int64), "feasible": np.empty(B, dtype=np.uint8)}
         res["pageable_ms"] = timed(lambda k: eng.eval_batch(Xp[k % 4], out=outp))
         del Xp
+        # candidates on the MADS mesh (granularity 1.0 on every variable, src/TDM_STATIC_opt.jl:131-137), sent as
+        # int16 mesh indices through cov_eval_batch_packed: a quarter of the bytes over PCIe, the same doubles in
+        # the kernels.  Same call shape as above (pinned buffers; winner + exchange when there are several ranks).
+        synth = cov.synth
+        Qh = [eng.pinned((B, 3 * N), np.int16) for _ in range(HOST_SETS)]
+        for k in range(HOST_SETS):
+            synth.mesh_candidates(B, N, seed=5000 + 97 * c.rank + k, out=Qh[k])
+
+        def call_mesh(k):
+            if c.world == 1:
+                eng.eval_batch_packed(Qh[k % HOST_SETS], 1.0, out=out)
+                return
+            r = eng.eval_batch_packed(Qh[k % HOST_SETS], 1.0, best=True, barrier=True, out=out)
+            bo, bi = r["best"]
+            cdist.exchange_winner(bo, bi, c.rank * B, scratch)
+
+        res["mesh_ms"] = timed(call_mesh)
+        # the packed call against cov_eval_batch on the widened matrix (all of one set), bit for bit
+        call_mesh(0)
+        got = {k: np.array(v) for k, v in out.items()}
+        wide = eng.eval_batch(Qh[0].astype(np.float64))
+        res["mesh_same"] = float(all(np.array_equal(got[k], wide[k]) for k in ("obj", "count", "feasible")))
+        res["mesh_sample"] = (Qh[0][:2048].copy(), got["obj"][:2048].copy(), got["count"][:2048].copy())
         if c.world > 1:
             # gather-the-objective-vector variant: double-buffered H2D (copy stream) -> kernel -> NCCL
             # all_gather_into_tensor of the objective slices -> D2H of the gathered vector (pinned)
@@ -486,10 +509,13 @@ def e2e_runs(c, eng, cov, wl, B, launches, steps, warmup):
                 gather_step(s)
             barrier(c)
             res["gather_ms"] = (time.perf_counter() - t0) * 1e3
+    sample = res.pop("mesh_sample")
+    same = res.pop("mesh_same")
     keys = sorted(res)
     vals = max_over_ranks(c, [res[k] for k in keys])
     res = dict(zip(keys, vals))
     res["winner_exchanges"] = len(winners)
+    res["mesh_same"], res["mesh_sample"] = bool(same), sample
     return res
 
 
@@ -696,6 +722,21 @@ def main():
             line["e2e_pageable"] = {"value": total / (e["pageable_ms"] * 1e-3), "unit": UNIT,
                                     "ms_per_call": e["pageable_ms"] / calls,
                                     "buffers": "pageable NumPy arrays in and out (what a Julia Vector is)"}
+            Qs, obj_s, cnt_s = e["mesh_sample"]
+            from oracle import c_oracle  # the checker only: 2048 mesh candidates of the timed sets against the C port
+            want = c_oracle.eval_batch(Qs.astype(np.float64), N, r_max, synth.points_from_bits(bits, wl["grid"], d, d),
+                                       sep_min=wl["sep"])
+            line["e2e_mesh"] = {"value": total / (e["mesh_ms"] * 1e-3), "unit": UNIT, "ms_per_call": e["mesh_ms"] / calls,
+                                "h2d_bytes_per_step": B * 3 * N * 2 * L, "d2h_bytes_per_step": B * 17 * L,
+                                "buffers": "pinned (cov_host_alloc)",
+                                "candidates": "uniform on the MADS mesh of the reference (granularity 1.0 on x, y and R, "
+                                              "src/TDM_STATIC_opt.jl:131-137), passed as int16 mesh indices to "
+                                              "cov_eval_batch_packed and widened to Float64 on the device",
+                                "exchange": "as e2e",
+                                "parity_on_sample": bool(e["mesh_same"] and np.array_equal(obj_s, want["obj"]) and
+                                                         np.array_equal(cnt_s, want["count"])),
+                                "parity_sample": "a whole 1M set bit for bit against cov_eval_batch on the widened "
+                                                 "Float64 matrix; 2048 of them against the C port"}
             if "noexch_ms" in e:
                 line["e2e_no_exchange"] = {"value": total / (e["noexch_ms"] * 1e-3), "unit": UNIT,
                                            "ms_per_call": e["noexch_ms"] / calls,

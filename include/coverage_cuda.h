@@ -34,7 +34,8 @@
 extern "C" {
 #endif
 
-#define COV_ABI_VERSION 2 /* 2: COV_OPT_PROGRESSIVE_INDEX, COV_KERNEL_ORDERED, cov_get_class_weights, cov_eval_batch_best */
+#define COV_ABI_VERSION 3 /* 2: COV_OPT_PROGRESSIVE_INDEX, COV_KERNEL_ORDERED, cov_get_class_weights, cov_eval_batch_best;
+                             3: cov_eval_batch_packed (COV_PACK_*) */
 
 #if defined(__GNUC__)
 #define COV_API __attribute__((visibility("default")))
@@ -217,6 +218,23 @@ COV_API int cov_argmin(cov_handle *h, const double *X, int64_t B, int32_t barrie
  * when the candidates of one poll are sharded over several GPUs. */
 COV_API int cov_eval_batch_best(cov_handle *h, const double *X, int64_t B, double *obj, int64_t *count,
                         uint8_t *feasible, int32_t barrier, double *best_obj, int64_t *best_idx);
+
+/* The same evaluation for candidates that sit on a mesh, sent PACKED: the trial points of a MADS poll / search step
+ * are x = q * granularity with integer q (granularity 1.0 on every variable in the reference,
+ * src/TDM_STATIC_opt.jl:131-137), so 2 or 4 bytes per variable can cross PCIe instead of 8 -- the end-to-end rate
+ * of cov_eval_batch is the PCIe rate. Q: B x 3N values in the candidate layout above, of type
+ *   COV_PACK_I16  int16_t,  value = (double)q * granularity   (one correctly rounded FP64 multiply; exact
+ *   COV_PACK_I32  int32_t,  value = (double)q * granularity    whenever granularity is a power of two)
+ *   COV_PACK_F32  float,    value = (double)q                  (granularity ignored)
+ * The device widens every slice into the Float64 matrix the kernels read, so the results are bit for bit those of
+ * cov_eval_batch on the widened matrix. The caller vouches that its Float64 trial points ARE these values (integers
+ * and FP32-representable numbers always are); nothing is rounded on the way in. obj / count / feasible as in
+ * cov_eval_batch (obj may be NULL when a winner is asked for); best_obj and best_idx both NULL, or both given:
+ * the poll winner as in cov_eval_batch_best. Pinned Q (cov_host_alloc) is DMA'd in place. */
+enum { COV_PACK_F32 = 1, COV_PACK_I32 = 2, COV_PACK_I16 = 3 };
+COV_API int cov_eval_batch_packed(cov_handle *h, const void *Q, int32_t pack, double granularity, int64_t B,
+                          double *obj, int64_t *count, uint8_t *feasible, int32_t barrier, double *best_obj,
+                          int64_t *best_idx);
 
 /* A whole MADS solve in native code: the batch producer the reference lacks (DirectSearch.jl evaluates one
  * trial point per call). Settings of TDM_STATIC_opt.optimize (src/TDM_STATIC_opt.jl:118-222): start point x0

@@ -68,10 +68,16 @@ class AreaMaxObjective:
             eng.param_owner = key
         return res, eng
 
-    def batch(self, X, want_feasible=False):
+    def batch(self, X, want_feasible=False, granularity=1.0):
         """Objective of every row of X (B x 3N).  With want_feasible also the fused extreme
-        constraints' verdicts."""
+        constraints' verdicts.  An int16 / int32 X holds MESH INDICES (candidate = q * granularity, the MADS mesh of
+        src/TDM_STATIC_opt.jl:131-137) and a float32 X values: they travel packed (cov_eval_batch_packed) and are
+        widened to Float64 on the device."""
         res, eng = self._engine()
+        if isinstance(X, np.ndarray) and X.dtype in (np.int16, np.int32, np.float32):
+            out = eng.eval_batch_packed(X.reshape(-1, 3 * self.N), granularity, want_count=False,
+                                        want_feasible=want_feasible)
+            return (out["obj"], out["feasible"].astype(bool)) if want_feasible else out["obj"]
         X = np.ascontiguousarray(X, dtype=np.float64).reshape(-1, 3 * self.N)
         # (non-dyadic weights, where the Float64 sum depends on the list order, are replayed in list order on the
         # device by the library's ordered kernel: nothing special here)

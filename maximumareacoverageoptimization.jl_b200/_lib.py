@@ -23,6 +23,7 @@ COV_ERR_NOMEM = -6
 KERNEL_AUTO, KERNEL_SPAN, KERNEL_BRUTE, KERNEL_EXACT, KERNEL_SPAN_GENERAL, KERNEL_ORDERED = 0, 1, 2, 3, 4, 5
 OPT_KERNEL, OPT_WARPS_PER_CTA, OPT_CTAS_PER_SM, OPT_BAND_ROWS, OPT_FORCE_EXACT, OPT_CHUNK, OPT_TRACE, OPT_ZEROCOPY_OUT, OPT_PLANE_MODE = 1, 2, 3, 4, 5, 6, 7, 8, 9
 OPT_PROGRESSIVE_INDEX = 10
+PACK_F32, PACK_I32, PACK_I16 = 1, 2, 3
 
 
 class GridInfo(C.Structure):
@@ -72,6 +73,7 @@ SIGNATURES = {
     "cov_eval_batch_device": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "cov_eval_one": (_i, [_vp, _vp, _pd]),
     "cov_eval_batch_best": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, C.c_int32, _pd, _pi64]),
+    "cov_eval_batch_packed": (_i, [_vp, _vp, C.c_int32, _d, _i64, _vp, _vp, _vp, C.c_int32, _pd, _pi64]),
     "cov_argmin": (_i, [_vp, _vp, _i64, C.c_int32, _pd, _pi64]),
     "cov_union_area_batch": (_i, [_vp, _vp, _i64, _i64, _vp]),
     "cov_mads_solve": (_i, [_vp, _vp, _i64, _d, C.c_uint64, _vp, _pd, _pi64]),

@@ -171,6 +171,7 @@ struct cov_handle {
     bool have_fire = false;
     // evaluation window (device) and staging (pinned host)
     DevBuf dX, d_obj, d_count, d_feas, d_clscnt, d_prog;
+    DevBuf d_raw[2]; // packed slices as they arrive (cov_eval_batch_packed), widened into dX
     void *h_in[2] = {nullptr, nullptr};
     size_t h_in_cap = 0;
     void *h_out = nullptr;
@@ -422,7 +423,7 @@ extern "C" void cov_destroy(cov_handle *h)
     DevBuf *bufs[] = {&h->mult, &h->cls, &h->planes, &h->planes_q, &h->params, &h->counter, &h->stats, &h->xyT,
                       &h->small_in, &h->argmin_obj, &h->argmin_idx, &h->removed, &h->overflow, &h->dX,
                       &h->d_obj, &h->d_count, &h->d_feas, &h->d_clscnt, &h->d_prog, &h->fire[0], &h->fire[1], &h->fire_p,
-                      &h->backup, &h->ent_cell, &h->ent_cls};
+                      &h->backup, &h->ent_cell, &h->ent_cls, &h->d_raw[0], &h->d_raw[1]};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (int k = 0; k < 2; ++k)
@@ -1381,11 +1382,34 @@ struct BestReq {
     int64_t idx = -1;
 };
 
+// Packed candidates (cov_eval_batch_packed): `elem`-byte values that the device widens to doubles, value * g.
+struct PackedIn {
+    const void *Q;
+    int pack;
+    double g;
+    size_t elem;
+};
+static void unpack_host(const PackedIn &pk, size_t n, double *out) // the same arithmetic as unpack_kernel, for poll sets
+{
+    switch (pk.pack) {
+    case COV_PACK_F32:
+        for (size_t k = 0; k < n; ++k) out[k] = (double)((const float *)pk.Q)[k];
+        break;
+    case COV_PACK_I32:
+        for (size_t k = 0; k < n; ++k) out[k] = (double)((const int32_t *)pk.Q)[k] * pk.g;
+        break;
+    default:
+        for (size_t k = 0; k < n; ++k) out[k] = (double)((const int16_t *)pk.Q)[k] * pk.g;
+        break;
+    }
+}
+
 static int eval_host(cov_handle *h, const double *X, int64_t B, double *obj, int64_t *count, uint8_t *feasible,
-                     int64_t *class_count, double *progressive, BestReq *best = nullptr)
+                     int64_t *class_count, double *progressive, BestReq *best = nullptr, const PackedIn *pk = nullptr)
 {
     OK(check_ready(h, "cov_eval_batch"));
-    if (B < 0 || (B > 0 && (!X || (!obj && !best)))) return fail(h, COV_ERR_INVALID, "cov_eval_batch: bad arguments");
+    if (B < 0 || (B > 0 && ((pk ? !pk->Q : !X) || (!obj && !best))))
+        return fail(h, COV_ERR_INVALID, "cov_eval_batch: bad arguments");
     if (progressive && h->o.prog_which > h->o.N)
         return fail(h, COV_ERR_INVALID, "cov_eval_batch_ex: COV_OPT_PROGRESSIVE_INDEX names UAV " +
                                             std::to_string(h->o.prog_which) + " but N = " + std::to_string(h->o.N));
@@ -1394,12 +1418,16 @@ static int eval_host(cov_handle *h, const double *X, int64_t B, double *obj, int
     const int N = h->o.N;
     const int ncls = h->g.n_classes;
     const size_t row_bytes = (size_t)3 * N * 8;
-    if (!best && (size_t)B * row_bytes <= (256u << 10) && (size_t)B * (25 + 8 * (size_t)ncls) <= (1536u << 10) && h->chunk == 0)
-        return eval_host_small(h, X, B, obj, count, feasible, class_count, progressive);
+    if (!best && (size_t)B * row_bytes <= (256u << 10) && (size_t)B * (25 + 8 * (size_t)ncls) <= (1536u << 10) && h->chunk == 0) {
+        if (!pk) return eval_host_small(h, X, B, obj, count, feasible, class_count, progressive);
+        std::vector<double> wide((size_t)B * 3 * N); // a poll set: widened on the host, then the poll path as it is
+        unpack_host(*pk, wide.size(), wide.data());
+        return eval_host_small(h, wide.data(), B, obj, count, feasible, class_count, progressive);
+    }
 #if COV_ZC_MID_LIMIT > 0
     // mid-size batches in pinned buffers: one launch that reads the candidates straight over PCIe (the
     // kernel's own unit prefetch overlaps transfer and compute) and writes the results back the same way
-    if (!best && h->zero_copy_out && h->chunk == 0 && N <= 8 && (size_t)B * row_bytes <= (size_t)(COV_ZC_MID_LIMIT) && is_pinned_host(X) &&
+    if (!pk && !best && h->zero_copy_out && h->chunk == 0 && N <= 8 && (size_t)B * row_bytes <= (size_t)(COV_ZC_MID_LIMIT) && is_pinned_host(X) &&
         is_pinned_host(obj) && (!count || is_pinned_host(count)) && (!feasible || is_pinned_host(feasible)) &&
         (!class_count || is_pinned_host(class_count)) && (!progressive || is_pinned_host(progressive))) {
         const double *vx = (const double *)device_view((void *)X);
@@ -1419,22 +1447,34 @@ static int eval_host(cov_handle *h, const double *X, int64_t B, double *obj, int
 #endif
     // device window: at most ~1 GiB of candidates at a time
     const int64_t window = std::max<int64_t>(1, std::min<int64_t>(B, (int64_t)((1ull << 30) / row_bytes)));
-    // slice size: ~16 MiB of candidates, a multiple of 32 candidates (keeps device slices 16-byte aligned)
-    int64_t chunk = h->chunk > 0 ? h->chunk : std::max<int64_t>(1024, (int64_t)((16ull << 20) / row_bytes) / 32 * 32);
+    // slice size: ~16 MiB of candidates, a multiple of 32 candidates (keeps device slices 16-byte aligned).
+    // Packed input is compute-bound, not PCIe-bound (5 UAVs, int16: 0.54 ms of copies beside 0.7 ms of kernels per
+    // 1 M candidates), so fewer, larger slices win: ~32 MiB of widened candidates (measured on B200, 1 M x 5 UAVs:
+    // int16 1.126 -> 1.098 ms per call, int32 / float32 1.51 -> 1.37 ms; tools/packed_exp.py)
+    const size_t slice_bytes = pk ? (32ull << 20) : (16ull << 20);
+    int64_t chunk = h->chunk > 0 ? h->chunk : std::max<int64_t>(1024, (int64_t)(slice_bytes / row_bytes) / 32 * 32);
     chunk = std::min(chunk, window);
+    // (two experiments lost here, DESIGN.md 5: a quarter- and a half-size first slice so that the kernels start sooner,
+    // 1.107 -> 1.125 ms; and no copy engine at all, the widening kernel reading the pinned buffer over PCIe beside the
+    // previous slice's objective kernel, 1.107 -> 1.21 ms)
     OK(ensure(h, h->dX, (size_t)window * row_bytes));
     OK(ensure(h, h->d_obj, (size_t)window * 8));
     if (count) OK(ensure(h, h->d_count, (size_t)window * 8));
     if (feasible || best) OK(ensure(h, h->d_feas, (size_t)window));
     if (class_count) OK(ensure(h, h->d_clscnt, (size_t)window * 8 * ncls));
     if (progressive) OK(ensure(h, h->d_prog, (size_t)window * 8));
-    const bool in_pinned = is_pinned_host(X);
+    // what crosses PCIe per candidate: the doubles themselves, or the packed values (widened on the device)
+    const size_t in_row_bytes = pk ? (size_t)3 * N * pk->elem : row_bytes;
+    const char *in_base = pk ? (const char *)pk->Q : (const char *)X;
+    const bool in_pinned = is_pinned_host(in_base);
     if (!in_pinned)
         for (int k = 0; k < 2; ++k) {
             size_t cap = h->h_in_cap;
-            OK(ensure_pinned(h, &h->h_in[k], &cap, (size_t)chunk * row_bytes));
+            OK(ensure_pinned(h, &h->h_in[k], &cap, (size_t)chunk * in_row_bytes));
             if (k == 1) h->h_in_cap = cap;
         }
+    if (pk)
+        for (int k = 0; k < 2; ++k) OK(ensure(h, h->d_raw[k], (size_t)chunk * in_row_bytes));
     // outputs that are not pinned are staged per window and copied out at the window's end
     const bool obj_p = !obj || is_pinned_host(obj), cnt_p = !count || is_pinned_host(count),
                fea_p = !feasible || is_pinned_host(feasible), cls_p = !class_count || is_pinned_host(class_count),
@@ -1450,13 +1490,16 @@ static int eval_host(cov_handle *h, const double *X, int64_t B, double *obj, int
     char *so = (char *)h->h_out;
 
     cudaEvent_t ev_in = get_event(h), ev_k = get_event(h), ev_free[2] = {get_event(h), get_event(h)};
-    bool free_armed[2] = {false, false};
+    cudaEvent_t ev_raw[2] = {get_event(h), get_event(h)}; // packed input: slot k of d_raw has been widened
+    bool free_armed[2] = {false, false}, raw_armed[2] = {false, false};
     int rc = COV_OK;
     auto done = [&](int code) {
         h->ev_pool.push_back(ev_in);
         h->ev_pool.push_back(ev_k);
         h->ev_pool.push_back(ev_free[0]);
         h->ev_pool.push_back(ev_free[1]);
+        h->ev_pool.push_back(ev_raw[0]);
+        h->ev_pool.push_back(ev_raw[1]);
         return code;
     };
 #define CKD(call)                                                         \
@@ -1485,14 +1528,16 @@ static int eval_host(cov_handle *h, const double *X, int64_t B, double *obj, int
         for (int64_t c0 = 0; c0 < wn; c0 += cn, slot ^= 1) {
             const int64_t left = wn - c0;
             cn = std::min(chunk, left);
-            const double *src = X + (size_t)(w0 + c0) * 3 * N;
+            const char *src = in_base + (size_t)(w0 + c0) * in_row_bytes;
             double *dst = (double *)h->dX.p + (size_t)c0 * 3 * N;
             if (!in_pinned) {
                 if (free_armed[slot]) CKD(cudaEventSynchronize(ev_free[slot]));
-                host_copy(h, h->h_in[slot], src, (size_t)cn * row_bytes);
-                src = (const double *)h->h_in[slot];
+                host_copy(h, h->h_in[slot], src, (size_t)cn * in_row_bytes);
+                src = (const char *)h->h_in[slot];
             }
-            CKD(cudaMemcpyAsync(dst, src, (size_t)cn * row_bytes, cudaMemcpyHostToDevice, h->s_in));
+            if (pk && raw_armed[slot]) CKD(cudaStreamWaitEvent(h->s_in, ev_raw[slot], 0)); // slot widened: reusable
+            CKD(cudaMemcpyAsync(pk ? h->d_raw[slot].p : (void *)dst, src, (size_t)cn * in_row_bytes, cudaMemcpyHostToDevice,
+                                h->s_in));
             if (!in_pinned) {
                 CKD(cudaEventRecord(ev_free[slot], h->s_in));
                 free_armed[slot] = true;
@@ -1501,6 +1546,12 @@ static int eval_host(cov_handle *h, const double *X, int64_t B, double *obj, int
             tr(h->s_in);
             CKD(cudaStreamWaitEvent(h->stream, ev_in, 0));
             tr(h->stream);
+            if (pk) {
+                CKD(launch_unpack(h->d_raw[slot].p, pk->pack, pk->g, dst, (long long)cn * 3 * N, h->stream));
+                h->launches += 1;
+                CKD(cudaEventRecord(ev_raw[slot], h->stream));
+                raw_armed[slot] = true;
+            }
             EvalOut out{};
             const int64_t g0 = w0 + c0;
             bool zc = h->zero_copy_out != 0 && (obj != nullptr || !best); // (cov_argmin has no per-candidate outputs)
@@ -1616,6 +1667,27 @@ extern "C" int cov_eval_batch_best(cov_handle *h, const double *X, int64_t B, do
     if (!best_obj || !best_idx) return fail(h, COV_ERR_INVALID, "cov_eval_batch_best: NULL winner outputs");
     BestReq br{barrier};
     OK(eval_host(h, X, B, obj, count, feasible, nullptr, nullptr, &br));
+    *best_obj = br.idx >= 0 ? br.best : INFINITY;
+    *best_idx = br.idx;
+    return COV_OK;
+}
+
+extern "C" int cov_eval_batch_packed(cov_handle *h, const void *Q, int32_t pack, double granularity, int64_t B, double *obj,
+                                     int64_t *count, uint8_t *feasible, int32_t barrier, double *best_obj,
+                                     int64_t *best_idx)
+{
+    if (!h) return fail(nullptr, COV_ERR_INVALID, "NULL handle");
+    DeviceGuard dg(h->device);
+    const size_t elem = pack == COV_PACK_F32 || pack == COV_PACK_I32 ? 4 : pack == COV_PACK_I16 ? 2 : 0;
+    if (!elem) return fail(h, COV_ERR_INVALID, "cov_eval_batch_packed: pack must be COV_PACK_F32, _I32 or _I16");
+    if (pack != COV_PACK_F32 && !(granularity > 0 && std::isfinite(granularity)))
+        return fail(h, COV_ERR_INVALID, "cov_eval_batch_packed: granularity must be a positive finite number");
+    if ((best_obj == nullptr) != (best_idx == nullptr))
+        return fail(h, COV_ERR_INVALID, "cov_eval_batch_packed: best_obj and best_idx go together");
+    PackedIn pk{Q, pack, granularity, elem};
+    if (!best_obj) return eval_host(h, nullptr, B, obj, count, feasible, nullptr, nullptr, nullptr, &pk);
+    BestReq br{barrier};
+    OK(eval_host(h, nullptr, B, obj, count, feasible, nullptr, nullptr, &br, &pk));
     *best_obj = br.idx >= 0 ? br.best : INFINITY;
     *best_idx = br.idx;
     return COV_OK;

@@ -503,6 +503,67 @@ cudaError_t launch_generate(double *dX, long long B, int N, unsigned long long s
     return cudaGetLastError();
 }
 
+// ---- packed candidates (cov_eval_batch_packed): mesh indices or FP32 values widened to the Float64 matrix the
+// objective kernels read.  MADS trial points sit on a granular mesh (granularity 1.0 on every variable in the
+// reference, src/TDM_STATIC_opt.jl:131-137), so a candidate is q * granularity with small integers q: 2 or 4 bytes per
+// variable cross PCIe instead of 8 and the value the kernels see is the same double (one exact conversion, one
+// correctly rounded multiply -- exact itself when granularity is a power of two or the product fits 53 bits).
+// HBM-bound and tiny beside the objective kernel: 4 elements per thread when both sides are 16-byte aligned.
+template <typename T>
+__device__ __forceinline__ double unpack_one(T v, double g)
+{
+    return __dmul_rn((double)v, g);
+}
+template <>
+__device__ __forceinline__ double unpack_one<float>(float v, double)
+{
+    return (double)v;
+}
+template <typename T, typename V4, bool VEC>
+__global__ void unpack_kernel(const T *__restrict__ in, double *__restrict__ out, long long n, double g)
+{
+    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    if (VEC) {
+        const long long n4 = n >> 2;
+        for (long long i = tid; i < n4; i += stride) {
+            const V4 v = reinterpret_cast<const V4 *>(in)[i];
+            double2 a, b;
+            a.x = unpack_one<T>(v.x, g);
+            a.y = unpack_one<T>(v.y, g);
+            b.x = unpack_one<T>(v.z, g);
+            b.y = unpack_one<T>(v.w, g);
+            reinterpret_cast<double2 *>(out)[2 * i] = a;
+            reinterpret_cast<double2 *>(out)[2 * i + 1] = b;
+        }
+        const long long t = (n4 << 2) + tid; // the last n % 4 elements
+        if (t < n) out[t] = unpack_one<T>(in[t], g);
+    } else {
+        for (long long i = tid; i < n; i += stride) out[i] = unpack_one<T>(in[i], g);
+    }
+}
+template <typename T, typename V4>
+static cudaError_t launch_unpack_t(const void *raw, double g, double *out, long long n, cudaStream_t s)
+{
+    const bool vec = (((uintptr_t)raw | (uintptr_t)out) & 15u) == 0;
+    const int block = 256;
+    const long long items = vec ? (n + 3) / 4 : n;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((items + block - 1) / block, 148 * 16));
+    if (vec) unpack_kernel<T, V4, true><<<grid, block, 0, s>>>((const T *)raw, out, n, g);
+    else unpack_kernel<T, V4, false><<<grid, block, 0, s>>>((const T *)raw, out, n, g);
+    return cudaGetLastError();
+}
+cudaError_t launch_unpack(const void *raw, int pack, double g, double *out, long long n, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    switch (pack) {
+    case 1: return launch_unpack_t<float, float4>(raw, g, out, n, s);
+    case 2: return launch_unpack_t<int, int4>(raw, g, out, n, s);
+    case 3: return launch_unpack_t<short, short4>(raw, g, out, n, s);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
 
 // ---- continuous variant: exact area of the union of the discs of a candidate ----
 // Boundary integration (Green's theorem): for every circle, the arcs that lie inside no other disc

@@ -77,5 +77,7 @@ cudaError_t launch_fire_seed(const unsigned char *state, unsigned char *mult, un
 cudaError_t launch_generate(double *dX, long long B, int N, unsigned long long seed, long long first,
                             double lx, double ly, double h_min, double h_max, double tan_half_fov,
                             cudaStream_t s);
+// n packed candidate values (pack: COV_PACK_F32 / _I32 / _I16 of coverage_cuda.h) -> doubles: value * g (FP32: value)
+cudaError_t launch_unpack(const void *raw, int pack, double g, double *out, long long n, cudaStream_t s);
 
 } // namespace cov

@@ -117,6 +117,21 @@ def random_candidates(B: int, N: int, seed: int, h_min: float = 5.0, h_max: floa
     return X
 
 
+def mesh_candidates(B: int, N: int, seed: int, granularity: float = 1.0, dtype=np.int16, h_min: float = 5.0,
+                    h_max: float = 30.0, tan_half_fov: float = TAN_HALF_FOV_DEFAULT, domain: float = DOMAIN,
+                    out=None) -> np.ndarray:
+    """The same distribution on the MADS mesh (granularity 1.0 on every variable in the reference,
+    src/TDM_STATIC_opt.jl:131-137): mesh INDICES q, uniform over the index ranges of x, y in [0, 500] and
+    R in [h_min, h_max]*tan(50 deg); the candidate is q * granularity.  dtype int16 / int32 (or float32: q itself)."""
+    rng = np.random.default_rng(np.random.PCG64(seed))
+    Q = out if out is not None else np.empty((B, 3 * N), dtype=dtype)
+    hi = int(math.floor(domain / granularity))
+    r_lo, r_hi = int(math.ceil(h_min * tan_half_fov / granularity)), int(math.floor(h_max * tan_half_fov / granularity))
+    Q[:, :2 * N] = rng.integers(0, hi + 1, (B, 2 * N))
+    Q[:, 2 * N:] = rng.integers(r_lo, r_hi + 1, (B, N))
+    return Q
+
+
 # ---- Philox4x32-10, the counter-based stream of cov_generate_candidates ----
 _M0, _M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
 _W0, _W1 = 0x9E3779B9, 0xBB67AE85

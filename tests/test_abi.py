@@ -24,7 +24,7 @@ def test_header_symbols_exported(cov):
     for n in names:
         assert hasattr(raw, n), f"{n} declared in include/coverage_cuda.h but not exported"
     assert set(names) == set(cov._lib.SIGNATURES), set(names) ^ set(cov._lib.SIGNATURES)
-    assert cov._lib.lib.cov_abi_version() == 2
+    assert cov._lib.lib.cov_abi_version() == 3
 
 
 def test_no_oracle_in_product():

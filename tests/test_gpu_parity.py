@@ -980,6 +980,8 @@ def test_bench_line_contract(cov):
     assert d["roofline_hbm"]["bound"] == "hbm" and 0 < d["roofline_hbm"]["frac"] < 1.0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["parity_on_sample"] is True
     assert d["e2e"]["h2d_bytes_per_step"] == 3 * 50000 * 120 and d["e2e"]["value"] > 0 and d["e2e_pageable"]["value"] > 0
+    assert d["e2e_mesh"]["h2d_bytes_per_step"] == 3 * 50000 * 30 and d["e2e_mesh"]["value"] > 0
+    assert d["e2e_mesh"]["parity_on_sample"] is True
     ex = {e["workload"][:2]: e for e in d["extra_workloads"]}
     assert set(ex) == {"C3", "C4", "C1"} and all(e["parity_on_sample"] is True for e in ex.values())
     # the named configs at their bench batch sizes MUST carry a live issue fraction from the committed capture
@@ -1195,6 +1197,10 @@ def test_two_objectives_share_one_engine(cov, orc):
     assert np.array_equal(o1, orc.eval_batch(X, N, r1, pts)["obj"]) and np.array_equal(o1, o1b) and fe1.all()
     want2 = orc.eval_batch(X, N, r2, pts, pre=pre, d_lim=10.0, tan_half_fov=T)
     assert np.array_equal(o2, want2["obj"]) and np.array_equal(fe2, want2["feasible"].astype(bool))
+    # mesh indices through the same closure: an int16 matrix travels packed, same values as the Float64 one
+    Q = cov.synth.mesh_candidates(64, N, seed=4)
+    assert np.array_equal(f1.batch(Q), orc.eval_batch(Q.astype(np.float64), N, r1, pts)["obj"])
+    assert np.array_equal(f1.batch(Q, granularity=0.5), f1.batch(Q.astype(np.float64) * 0.5))
     cells.close()
 
 
@@ -1276,3 +1282,100 @@ def test_eval_batch_best_and_pipelined_argmin(cov, orc, engine):
     out = {"obj": engine.pinned((B,)), "count": engine.pinned((B,), np.int64), "feasible": engine.pinned((B,), np.uint8)}
     r = engine.eval_batch_best(Xp, out=out)
     assert np.array_equal(out["obj"], ref["obj"]) and r["best"] == (masked.min(), int(np.argmin(masked)))
+
+
+@pytest.mark.parametrize("dtype,g", [(np.int16, 1.0), (np.int16, 0.5), (np.int32, 0.1), (np.float32, 1.0)])
+def test_packed_candidates_match_the_widened_matrix(cov, orc, engine, dtype, g):
+    """cov_eval_batch_packed: mesh indices (int16 / int32, value = q * granularity) or float32 values, widened on the
+    device -- results bit for bit those of cov_eval_batch on the Float64 matrix (and of the oracle on it), on every
+    route: poll set (host-widened), sliced pipeline from pageable and from pinned memory, odd slice sizes, the winner."""
+    n = 256
+    d = 500.0 / n
+    bits, _ = cov.synth.fire_grid(n)
+    pts = cov.synth.points_from_bits(bits, n, d, d)
+    engine.set_grid_bits(bits, n, n, d, d)
+    N, B = 5, 150_001  # odd on purpose: the last slice is ragged, the element count is not a multiple of 4
+    r_max = np.full(N, 30 * T)
+    if dtype is np.float32:
+        Q = cov.synth.random_candidates(B, N, seed=31).astype(np.float32)
+        X = Q.astype(np.float64)
+    else:
+        Q = cov.synth.mesh_candidates(B, N, seed=31, granularity=g, dtype=dtype)
+        X = Q.astype(np.float64) * g
+    pre = X[0].copy()
+    engine.set_params(N, r_max, prev_xyR=pre, d_lim=200.0, tan_half_fov=T)
+    ref = engine.eval_batch(X)
+    assert 0 < ref["feasible"].sum() < B
+    want = orc.eval_batch(X[:600], N, r_max, pts, pre=pre, d_lim=np.full(N, 200.0), tan_half_fov=T)
+    for k in ("count", "feasible"):
+        assert np.array_equal(ref[k][:600], want[k])
+    assert same_doubles(ref["obj"][:600], want["obj"])
+
+    def check(r, nb=B):
+        assert same_doubles(r["obj"], ref["obj"][:nb])
+        assert np.array_equal(r["count"], ref["count"][:nb]) and np.array_equal(r["feasible"], ref["feasible"][:nb])
+
+    check(engine.eval_batch_packed(Q, g))                      # pageable, sliced pipeline
+    for nb in (1, 30, 2184):                                   # poll sets
+        check(engine.eval_batch_packed(Q[:nb], g), nb)
+    check(engine.eval_batch_packed(Q[:40_003], g), 40_003)     # one ragged slice (the mid-size route of the doubles)
+    masked = np.where(ref["feasible"].astype(bool), ref["obj"], np.inf)
+    r = engine.eval_batch_packed(Q, g, best=True)
+    check(r)
+    assert r["best"] == (masked.min(), int(np.argmin(masked)))
+    r = engine.eval_batch_packed(Q, g, best=True, barrier=False)
+    assert r["best"] == (ref["obj"].min(), int(np.argmin(ref["obj"])))
+    Qp = engine.pinned((B, 3 * N), dtype)                      # pinned: DMA'd in place, zero-copy results
+    Qp[:] = Q
+    out = {"obj": engine.pinned((B,)), "count": engine.pinned((B,), np.int64), "feasible": engine.pinned((B,), np.uint8)}
+    check(engine.eval_batch_packed(Qp, g, out=out))
+    for chunk in (999, 4097):                                  # odd slices: misaligned device slices (scalar widening)
+        engine.set_option(cov.OPT_CHUNK, chunk)
+        check(engine.eval_batch_packed(Q[:20_001], g), 20_001)
+    engine.set_option(cov.OPT_CHUNK, 0)
+    engine.set_option(cov.OPT_ZEROCOPY_OUT, 0)
+    check(engine.eval_batch_packed(Qp, g, out=out))
+    engine.set_option(cov.OPT_ZEROCOPY_OUT, 1)
+    if dtype is np.int16 and g == 1.0:                         # several full slices (both raw slots reused)
+        Bb = 700_001
+        Qb = cov.synth.mesh_candidates(Bb, N, seed=32, dtype=dtype)
+        big = engine.eval_batch(Qb.astype(np.float64))
+        r = engine.eval_batch_packed(Qb, g, best=True)
+        for k in ("obj", "count", "feasible"):
+            assert np.array_equal(r[k], big[k]), k
+        mb = np.where(big["feasible"].astype(bool), big["obj"], np.inf)
+        assert r["best"] == (mb.min(), int(np.argmin(mb))) or not np.isfinite(mb.min())
+
+
+def test_packed_candidates_large_swarm_and_errors(cov, orc, engine):
+    """The CTA-per-candidate kernel behind the packed entry (50 UAVs, cons8), and the argument checks."""
+    n = 256
+    d = 500.0 / n
+    bits, _ = cov.synth.fire_grid(n)
+    pts = cov.synth.points_from_bits(bits, n, d, d)
+    engine.set_grid_bits(bits, n, n, d, d)
+    N, B = 50, 6_000
+    r_max = np.full(N, 30 * T)
+    engine.set_params(N, r_max, sep_min=15.0)
+    Q = cov.synth.mesh_candidates(B, N, seed=7)
+    X = Q.astype(np.float64)
+    r = engine.eval_batch_packed(Q, 1.0)
+    want = orc.eval_batch(X[:200], N, r_max, pts, sep_min=15.0)
+    assert np.array_equal(r["count"][:200], want["count"]) and same_doubles(r["obj"][:200], want["obj"])
+    assert np.array_equal(r["feasible"][:200], want["feasible"])
+    ref = engine.eval_batch(X)
+    assert same_doubles(r["obj"], ref["obj"]) and np.array_equal(r["count"], ref["count"])
+    import ctypes as C
+    lib, h = cov._lib.lib, engine.handle
+    obj = np.empty(4)
+    bo, bi = C.c_double(), C.c_int64()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    assert lib.cov_eval_batch_packed(h, p(Q), 9, 1.0, 4, p(obj), None, None, 1, None, None) == cov._lib.COV_ERR_INVALID
+    assert lib.cov_eval_batch_packed(h, p(Q), 3, 0.0, 4, p(obj), None, None, 1, None, None) == cov._lib.COV_ERR_INVALID
+    assert lib.cov_eval_batch_packed(h, p(Q), 3, math.nan, 4, p(obj), None, None, 1, None, None) == cov._lib.COV_ERR_INVALID
+    assert lib.cov_eval_batch_packed(h, p(Q), 3, 1.0, 4, p(obj), None, None, 1, C.byref(bo), None) == cov._lib.COV_ERR_INVALID
+    assert lib.cov_eval_batch_packed(h, None, 3, 1.0, 4, p(obj), None, None, 1, None, None) == cov._lib.COV_ERR_INVALID
+    assert lib.cov_eval_batch_packed(h, p(Q), 3, 1.0, 4, None, None, None, 1, None, None) == cov._lib.COV_ERR_INVALID
+    assert lib.cov_eval_batch_packed(h, p(Q), 3, 1.0, 0, p(obj), None, None, 1, None, None) == cov._lib.COV_OK
+    assert lib.cov_eval_batch_packed(h, p(Q), 3, 1.0, 4, None, None, None, 1, C.byref(bo), C.byref(bi)) == cov._lib.COV_OK
+    assert bi.value == int(np.argmin(np.where(ref["feasible"][:4].astype(bool), ref["obj"][:4], np.inf))) or bi.value == -1
