@@ -101,3 +101,9 @@ def optimize(input, obj, cons_ext, cons_prog, N_iter, **kw):
     """src/TDM_STATIC_opt.jl:118-222 -- see mads.optimize."""
     from .mads import optimize as _opt
     return _opt(input, obj, cons_ext, cons_prog, N_iter, **kw)
+
+
+def optimize_multistart(inputs, obj, cons_ext, cons_prog, N_iter, **kw):
+    """Several solves in lockstep, one objective launch per iteration for all of them -- see mads.optimize_multistart."""
+    from .mads import optimize_multistart as _opt
+    return _opt(inputs, obj, cons_ext, cons_prog, N_iter, **kw)

@@ -104,45 +104,61 @@ def _snap(x, g):
     return np.where(g > 0, np.rint(x / np.where(g > 0, g, 1.0)) * g, x)
 
 
-def optimize(input, obj, cons_ext, cons_prog, N_iter, granularity=1.0, seed=None, snap_initial=False,
-             return_stats=False, native=None):
-    """src/TDM_STATIC_opt.jl:118-222.  `obj`: callable x -> float, preferably with `.batch(X)` (and
-    `.fuse(constraints)`, see TDM_STATIC_opt.AreaMaxObjective).  `cons_ext`: extreme constraints
-    x -> bool (flat list; nested lists as in FullSimulation.jl:86 `[cons_ext, cons3]` are flattened).
-    `cons_prog` is accepted and ignored exactly like the reference does (:154-159 is commented out).
-    Returns (result, runtime) -- with return_stats=True also a dict of counters.
+class _Solve:
+    """One MADS solve as a state machine: `poll()` hands out the next poll set, `update(P, f)` takes its objective
+    values (extreme barrier already applied: +inf where a constraint fails).  `optimize` drives one of these,
+    `optimize_multistart` many in lockstep."""
 
-    native: True runs the whole solve inside the library (cov_mads_solve: same algorithm and settings, its own
-    random stream, no Python between polls); it needs an objective made by createObjective on a list with
-    exactly summable weights and constraints that all fuse.  None (default) picks it when that holds."""
-    t_start = time.perf_counter()
-    if native is not False and hasattr(obj, "native_solver") and np.isscalar(granularity) and not snap_initial:
-        flat_c = []
-        for c in (cons_ext if isinstance(cons_ext, (list, tuple)) else [cons_ext]):
-            flat_c.extend(c if isinstance(c, (list, tuple)) else [c])
-        solver = obj.native_solver(flat_c)
-        if solver is not None:
-            x, fx, st = solver(np.ascontiguousarray(input, dtype=np.float64).ravel(), int(N_iter), float(granularity),
-                               0 if seed is None else int(seed))
-            runtime = time.perf_counter() - t_start
-            st["objective"] = fx
-            return (x, runtime, st) if return_stats else (x, runtime)
-        if native is True:
-            raise ValueError("native MADS needs fusable constraints and exactly summable weights")
-    x0 = np.ascontiguousarray(input, dtype=np.float64).ravel().copy()
-    n = x0.size
-    rng = np.random.default_rng(seed)
+    def __init__(self, x0, g, rng, snap_initial=False):
+        self.x0, self.g, self.rng = x0, g, rng
+        self.x = _snap(x0, g) if snap_initial else x0.copy()
+        self.fx = math.inf
+        self.mesh = None
+        self.feasible_found = False
+        self.done = False
+        self.iterations = 0
+        self.successes = 0
 
+    def start(self, fx: float):
+        self.fx = fx
+        self.mesh = _Mesh(self.x, self.g)
+        self.feasible_found = math.isfinite(fx)
+
+    def poll(self) -> np.ndarray:
+        self.iterations += 1
+        n = self.x.size
+        delta, Delta = self.mesh.mesh_size(), self.mesh.poll_size()
+        D = _poll_directions(n, np.maximum(np.rint(Delta / delta), 1.0), self.rng)
+        P = _snap(self.x[None, :] + D * delta[None, :], self.g)
+        P = P[np.any(P != self.x[None, :], axis=1)]
+        return np.unique(P, axis=0) if len(P) else P
+
+    def update(self, P: np.ndarray, f: np.ndarray):
+        k = int(np.argmin(f)) if len(P) else -1
+        best = float(f[k]) if len(P) else math.inf
+        if best < self.fx or (not self.feasible_found and math.isfinite(best)):
+            self.x, self.fx = P[k].copy(), best
+            self.feasible_found = True
+            self.successes += 1
+            self.mesh.enlarge()
+        elif not self.mesh.refine():
+            self.done = True  # every poll size is down at its granularity: the granular mesh cannot refine
+
+    def result(self) -> np.ndarray:
+        return self.x if self.feasible_found else self.x0  # p.x if there is a feasible incumbent, else the start (p.i)
+
+
+def _flatten_constraints(cons_ext):
     flat = []
     for c in (cons_ext if isinstance(cons_ext, (list, tuple)) else [cons_ext]):
         flat.extend(c if isinstance(c, (list, tuple)) else [c])
-    host_cons = obj.fuse(flat) if hasattr(obj, "fuse") else flat
+    return flat
 
-    stats = {"iterations": 0, "evaluations": 0, "batches": 0, "cache_hits": 0, "successes": 0}
-    cache = {}
 
+def _barrier_evaluator(obj, host_cons, stats, cache):
+    """P -> objective of every row with the extreme barrier (+inf where a constraint fails), ONE obj.batch call for
+    the rows not seen before."""
     def evaluate(P):
-        """Objective with the extreme barrier for every row of P: +inf where a constraint fails."""
         P = np.ascontiguousarray(P, dtype=np.float64)
         keys = [p.tobytes() for p in P]
         f = np.empty(len(P))
@@ -170,36 +186,100 @@ def optimize(input, obj, cons_ext, cons_prog, N_iter, granularity=1.0, seed=None
         for k in range(len(P)):
             f[k] = cache[keys[k]]
         return f
+    return evaluate
+
+
+def optimize(input, obj, cons_ext, cons_prog, N_iter, granularity=1.0, seed=None, snap_initial=False,
+             return_stats=False, native=None):
+    """src/TDM_STATIC_opt.jl:118-222.  `obj`: callable x -> float, preferably with `.batch(X)` (and
+    `.fuse(constraints)`, see TDM_STATIC_opt.AreaMaxObjective).  `cons_ext`: extreme constraints
+    x -> bool (flat list; nested lists as in FullSimulation.jl:86 `[cons_ext, cons3]` are flattened).
+    `cons_prog` is accepted and ignored exactly like the reference does (:154-159 is commented out).
+    Returns (result, runtime) -- with return_stats=True also a dict of counters.
+
+    native: True runs the whole solve inside the library (cov_mads_solve: same algorithm and settings, its own
+    random stream, no Python between polls); it needs an objective made by createObjective on a list with
+    exactly summable weights and constraints that all fuse.  None (default) picks it when that holds."""
+    t_start = time.perf_counter()
+    if native is not False and hasattr(obj, "native_solver") and np.isscalar(granularity) and not snap_initial:
+        solver = obj.native_solver(_flatten_constraints(cons_ext))
+        if solver is not None:
+            x, fx, st = solver(np.ascontiguousarray(input, dtype=np.float64).ravel(), int(N_iter), float(granularity),
+                               0 if seed is None else int(seed))
+            runtime = time.perf_counter() - t_start
+            st["objective"] = fx
+            return (x, runtime, st) if return_stats else (x, runtime)
+        if native is True:
+            raise ValueError("native MADS needs fusable constraints and exactly summable weights")
+    x0 = np.ascontiguousarray(input, dtype=np.float64).ravel().copy()
+    n = x0.size
+    rng = np.random.default_rng(seed)
+
+    flat = _flatten_constraints(cons_ext)
+    host_cons = obj.fuse(flat) if hasattr(obj, "fuse") else flat
+
+    stats = {"iterations": 0, "evaluations": 0, "batches": 0, "cache_hits": 0, "successes": 0}
+    evaluate = _barrier_evaluator(obj, host_cons, stats, {})
 
     g = np.asarray(granularity, dtype=np.float64) * np.ones(n)
-    x = _snap(x0, g) if snap_initial else x0.copy()
-    fx = float(evaluate(x[None, :])[0])
-    mesh = _Mesh(x, g)
-    feasible_found = math.isfinite(fx)
-
+    solve = _Solve(x0, g, rng, snap_initial)
+    solve.start(float(evaluate(solve.x[None, :])[0]))
     for _ in range(int(N_iter)):
-        stats["iterations"] += 1
-        delta, Delta = mesh.mesh_size(), mesh.poll_size()
-        D = _poll_directions(n, np.maximum(np.rint(Delta / delta), 1.0), rng)
-        P = _snap(x[None, :] + D * delta[None, :], g)
-        P = P[np.any(P != x[None, :], axis=1)]
-        if len(P):
-            P = np.unique(P, axis=0)
-            f = evaluate(P)
-            k = int(np.argmin(f))
-            best = float(f[k])
-        else:
-            best = math.inf
-        if best < fx or (not feasible_found and math.isfinite(best)):
-            x, fx = P[k].copy(), best
-            feasible_found = True
-            stats["successes"] += 1
-            mesh.enlarge()
-        elif not mesh.refine():
-            break  # every poll size is down at its granularity: the granular mesh cannot refine
+        P = solve.poll()
+        solve.update(P, evaluate(P) if len(P) else np.empty(0))
+        if solve.done:
+            break
+    stats["iterations"], stats["successes"] = solve.iterations, solve.successes
+    x, fx, feasible_found = solve.x, solve.fx, solve.feasible_found
     result = x if feasible_found else x0  # p.x if there is a feasible incumbent, else the start (p.i)
     runtime = time.perf_counter() - t_start
     stats["objective"] = fx
     if return_stats:
         return result, runtime, stats
     return result, runtime
+
+
+def optimize_multistart(inputs, obj, cons_ext, cons_prog, N_iter, granularity=1.0, seed=None, return_stats=False):
+    """S independent MADS solves from the rows of `inputs` (S x n), with the settings of `optimize`, advanced in
+    LOCKSTEP: at every iteration the poll sets of all the solves still running are concatenated and evaluated in ONE
+    `obj.batch` call (S x 2n trial points per launch instead of 2n -- SURVEY.md 8f-1's multi-start swarms: a 30-point
+    poll costs the GPU a launch whether it carries 30 candidates or 3 000).  Solve k draws its directions from
+    `default_rng(seed + k)`, so its iterates are exactly those of `optimize(inputs[k], ..., seed=seed + k,
+    native=False)`; lockstep changes how the work is batched, not what is computed.
+    Returns (results S x n, objectives S, runtime) -- results[k] is solve k's feasible incumbent, else its start;
+    objectives[k] is +inf where solve k never found a feasible point.  With return_stats=True also a dict of counters
+    (iterations = lockstep iterations, batches = obj.batch calls, per_solve_iterations, best = argmin of objectives)."""
+    t_start = time.perf_counter()
+    X0 = np.ascontiguousarray(inputs, dtype=np.float64)
+    if X0.ndim != 2 or not len(X0):
+        raise ValueError("inputs must be S x n with S >= 1")
+    S, n = X0.shape
+    flat = _flatten_constraints(cons_ext)
+    host_cons = obj.fuse(flat) if hasattr(obj, "fuse") else flat
+    stats = {"iterations": 0, "evaluations": 0, "batches": 0, "cache_hits": 0, "successes": 0}
+    evaluate = _barrier_evaluator(obj, host_cons, stats, {})
+    g = np.asarray(granularity, dtype=np.float64) * np.ones(n)
+    solves = [_Solve(X0[k].copy(), g, np.random.default_rng(None if seed is None else seed + k)) for k in range(S)]
+    for s, f0 in zip(solves, evaluate(np.stack([s.x for s in solves]))):
+        s.start(float(f0))
+    for _ in range(int(N_iter)):
+        active = [s for s in solves if not s.done]
+        if not active:
+            break
+        stats["iterations"] += 1
+        polls = [s.poll() for s in active]
+        rows = [len(P) for P in polls]
+        f = evaluate(np.concatenate(polls)) if sum(rows) else np.empty(0)
+        at = 0
+        for s, P, m in zip(active, polls, rows):
+            s.update(P, f[at:at + m])
+            at += m
+    results = np.stack([s.result() for s in solves])
+    objectives = np.array([s.fx if s.feasible_found else math.inf for s in solves])
+    runtime = time.perf_counter() - t_start
+    if return_stats:
+        stats["successes"] = sum(s.successes for s in solves)
+        stats["per_solve_iterations"] = [s.iterations for s in solves]
+        stats["best"] = int(np.argmin(objectives))
+        return results, objectives, runtime, stats
+    return results, objectives, runtime
