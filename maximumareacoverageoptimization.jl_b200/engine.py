@@ -396,6 +396,38 @@ class CoverageEngine:
         return ms.value, n.value
 
 
+def pack_candidates(X, granularity: float = 1.0, dtype=np.int16) -> np.ndarray:
+    """Mesh indices of a Float64 candidate matrix for `eval_batch_packed`, LOSSLESS or not at all: returns
+    Q = rint(X / granularity) as `dtype` (int16 / int32) after checking that Q * granularity reproduces every entry
+    of X exactly (dtype float32: that (double)(float)x == x); raises ValueError otherwise, naming the first
+    offending entry.  Pure NumPy (no device): the check costs more than the PCIe bytes it saves, so a caller that
+    works in mesh indices anyway (a MADS poll driver does) should keep them rather than call this per batch."""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    dtype = np.dtype(dtype)
+    if dtype == np.float32:
+        Q = X.astype(np.float32)
+        back = Q.astype(np.float64)
+    elif dtype in (np.dtype(np.int16), np.dtype(np.int32)):
+        if not (granularity > 0 and math.isfinite(granularity)):
+            raise ValueError("granularity must be a positive finite number")
+        q = np.rint(X / granularity)
+        info = np.iinfo(dtype)
+        bad = ~((q >= info.min) & (q <= info.max))  # (also catches NaN)
+        if bad.any():
+            k = np.argwhere(bad)[0]
+            raise ValueError(f"entry {tuple(int(v) for v in k)} = {X[tuple(k)]!r} does not fit {dtype.name} mesh indices")
+        Q = q.astype(dtype)
+        back = Q.astype(np.float64) * granularity
+    else:
+        raise TypeError("dtype must be int16, int32 or float32")
+    same = (back == X) | (np.isnan(back) & np.isnan(X))  # by value: -0.0 packs as +0, which no term of the objective can tell apart
+    if not same.all():
+        k = np.argwhere(~same)[0]
+        raise ValueError(f"entry {tuple(int(v) for v in k)} = {X[tuple(k)]!r} is not on the mesh of granularity "
+                         f"{granularity!r} ({dtype.name}): packing would change it")
+    return Q
+
+
 def threshold(R: float) -> float:
     """T(R): sqrt(s) < R  <=>  s < T(R) (the closed form the kernels use)."""
     return lib.cov_threshold(float(R))

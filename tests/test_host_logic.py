@@ -122,3 +122,40 @@ def test_bench_issue_roofline_helpers(tmp_path, monkeypatch):
         committed = json.load(f)
     assert {k.split("|")[0] for k in committed["kernels"]} >= {"c2", "c3", "c4"}
     assert len(bench.source_sha()) == 16 and bench.source_sha() == bench.source_sha()
+
+
+def test_pack_candidates_is_lossless_or_refuses(cov):
+    """Mesh indices for cov_eval_batch_packed: what the device computes from them, (double)q * granularity, must be the
+    caller's Float64 candidates bit for bit -- pack_candidates checks exactly that and refuses anything else."""
+    import pytest
+    from coverage_b200 import mads
+    rng = np.random.default_rng(3)
+    # trial points of the poll driver ARE on the mesh: _snap writes rint(v / g) * g, the same product the device forms
+    for g in (1.0, 0.5, 0.25, 0.1, 2.0):
+        P = mads._snap(rng.uniform(-50, 550, (400, 15)), np.full(15, g))
+        for dt in (np.int16, np.int32):
+            Q = cov.pack_candidates(P, g, dt)
+            assert Q.dtype == dt and np.array_equal(Q.astype(np.float64) * g, P)  # (by value: rint gives -0.0 too)
+    Q = cov.synth.mesh_candidates(1000, 5, seed=1)
+    assert np.array_equal(cov.pack_candidates(Q.astype(np.float64)), Q)
+    X = cov.synth.random_candidates(100, 5, seed=2)
+    with pytest.raises(ValueError, match="not on the mesh"):
+        cov.pack_candidates(X)                                   # random reals are not integers
+    with pytest.raises(ValueError, match="not on the mesh"):
+        cov.pack_candidates(X, dtype=np.float32)                 # nor FP32-representable
+    F = X.astype(np.float32).astype(np.float64)
+    assert np.array_equal(cov.pack_candidates(F, dtype=np.float32).astype(np.float64), F)
+    with pytest.raises(ValueError, match="does not fit"):
+        cov.pack_candidates(np.array([[40000.0, 1.0, 2.0]]))     # beyond int16
+    assert cov.pack_candidates(np.array([[40000.0, 1.0, 2.0]]), dtype=np.int32).tolist() == [[40000, 1, 2]]
+    with pytest.raises(ValueError):
+        cov.pack_candidates(np.array([[np.nan, 1.0, 2.0]]))
+    with pytest.raises(ValueError):
+        cov.pack_candidates(np.ones((1, 3)), granularity=0.0)
+    with pytest.raises(TypeError):
+        cov.pack_candidates(np.ones((1, 3)), dtype=np.int64)
+    # a granularity that is not a power of two: 0.1 * q is one rounded product on both sides, so values made that
+    # way pack; the same numbers typed in decimal may not (0.3 != 3 * 0.1 in binary64)
+    assert cov.pack_candidates(np.array([[3 * 0.1]]), 0.1).tolist() == [[3]]
+    with pytest.raises(ValueError, match="not on the mesh"):
+        cov.pack_candidates(np.array([[0.3]]), 0.1)
