@@ -62,9 +62,9 @@ def header_prototypes():
 def _split_top(s):
     out, depth, cur = [], 0, ""
     for ch in s:
-        if ch in "({":
+        if ch in "({[":
             depth += 1
-        elif ch in ")}":
+        elif ch in ")}]":
             depth -= 1
         if ch == "," and depth == 0:
             out.append(cur.strip())
@@ -85,7 +85,14 @@ def julia_ccalls():
         while depth:
             depth += {"(": 1, ")": -1}.get(text[k], 0)
             k += 1
-        calls.append((m.group(1), m.group(2), _split_top(text[start:k - 1]), text.count("\n", 0, m.start()) + 1))
+        types = _split_top(text[start:k - 1])
+        # the values handed over: everything between the type tuple and the ccall's closing parenthesis
+        depth, j = 1, k
+        while depth:
+            depth += {"(": 1, ")": -1, "[": 1, "]": -1}.get(text[j], 0)
+            j += 1
+        values = _split_top(text[k:j - 1].lstrip().lstrip(","))
+        calls.append((m.group(1), m.group(2), types, text.count("\n", 0, m.start()) + 1, values))
     return calls
 
 
@@ -102,7 +109,8 @@ def test_julia_ccalls_match_the_header():
     calls = julia_ccalls()
     assert len(calls) >= 25
     seen = set()
-    for name, ret, args, line in calls:
+    for name, ret, args, line, values in calls:
+        assert len(values) == len(args), f"CoverageCUDA.jl:{line}: {name}: {len(args)} argument types, {len(values)} values"
         assert name in protos, f"CoverageCUDA.jl:{line}: {name} is not declared in coverage_cuda.h"
         c_ret, c_args = protos[name]
         assert ret in C_RET_TO_JULIA[c_ret], f"CoverageCUDA.jl:{line}: {name} returns {c_ret}, ccall says {ret}"
